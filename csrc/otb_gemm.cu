@@ -1,0 +1,337 @@
+// otter_b200 — tcgen05 / TMA GEMM with fused epilogues (the >99.9 %-of-FLOPs kernel of the hot path).
+//
+//   D[M,N] = epilogue( A[M,K] . B[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM.
+//
+// Serves every nn.Linear on the path and its autograd dgrad / wgrad:
+//   forward  y  = x W^T      : A = x  [M][K]  K-major,  B = W  [N][K]  K-major
+//   dgrad    dx = dy W       : A = dy [M][N'] K-major,  B = W  [N'][K'] read as MN-major (no transpose copy)
+//   wgrad    dW = dy^T x     : A = dy read MN-major,    B = x  read MN-major (reduction over tokens)
+// (reference: modeling_otter.py:139-148,164-184,253-256,284-288,340,363-370; clip.py:106-149)
+//
+// Structure (one CTA per SM, persistent over output tiles, 256 threads):
+//   warp 0   : TMA producer   — cp.async.bulk.tensor 128B-swizzled tiles into a kStages-deep smem ring
+//   warp 1   : MMA issuer     — one thread issues tcgen05.mma (128 x BN x 16), tcgen05.commit frees smem slots
+//   warp 2   : TMEM allocator — 2 x BN fp32 columns (double-buffered accumulator)
+//   warps 4-7: epilogue       — tcgen05.ld 32 lanes x 32 columns, fused bias/GELU/gate/residual, 16 B stores
+// The accumulator double buffer lets the epilogue of tile i overlap the main loop of tile i+1.
+#include "otb_common.cuh"
+#include "otb_host.h"
+
+namespace otb {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 256;
+
+struct GemmEpi {
+  const float* bias;
+  const bf16* aux_in;
+  bf16* aux_out;
+  const float* scale_ptr;
+  const bf16* residual;
+  void* out;
+  long long ld_out, ld_aux_in, ld_aux_out, ld_res;
+  int act, scale_tanh, out_fp32, accumulate;
+  float alpha;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;            // 16 KB
+  static constexpr int kBBytes = BN * kBK * 2;             // 32 KB (BN=256) / 16 KB (BN=128)
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;                 // double-buffered accumulator
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
+                 int K, GemmEpi ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                        // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;    // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (M + kBM - 1) / kBM;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t % tiles_m) * kBM;
+      const int n0 = (t / tiles_m) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        const int k0 = kb * kBK;
+        if constexpr (!A_MN) {
+          tma_load_2d(sa, &map_a, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int c = 0; c < kBM / 64; ++c)                  // box {64 m, 64 k rows} per 64-wide chunk
+            tma_load_2d(sa + c * (kBK * 128), &map_a, &full_bar[stage], m0 + c * 64, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(sb, &map_b, &full_bar[stage], k0, n0);  // box {64 k, BN rows}
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(sb + c * (kBK * 128), &map_b, &full_bar[stage], n0 + c * 64, k0);
+        }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (single thread) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, A_MN, B_MN);
+    constexpr uint32_t a_lbo = A_MN ? kBK * 128 : 16, a_sbo = 1024, a_kstep = A_MN ? 2048 : 32;
+    constexpr uint32_t b_lbo = B_MN ? kBK * 128 : 16, b_sbo = 1024, b_kstep = B_MN ? 2048 : 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+        const uint64_t da = make_smem_desc(sa, a_lbo, a_sbo);
+        const uint64_t db = make_smem_desc(sb, b_lbo, b_sbo);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          umma_bf16(d_tmem, da + ((k * a_kstep) >> 4), db + ((k * b_kstep) >> 4), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);  // frees this smem slot once the MMAs above retire
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float scale = ep.alpha;
+    if (ep.scale_ptr != nullptr) {
+      const float s = __ldg(ep.scale_ptr);
+      scale *= ep.scale_tanh ? tanhf(s) : s;
+    }
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (t % tiles_m) * kBM;
+      const int n0 = (t / tiles_m) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int colbase = n0 + c * 32;
+        if (row_ok && colbase < N) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = colbase + g * 8;
+            if (col >= N) break;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+            if (ep.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (ep.aux_out != nullptr) {
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(ep.aux_out + static_cast<long long>(row) * ep.ld_aux_out + col) = o;
+            }
+            if (ep.act == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+            } else if (ep.act == 2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
+            }
+            if (ep.aux_in != nullptr) {
+              const uint4 a = __ldg(
+                  reinterpret_cast<const uint4*>(ep.aux_in + static_cast<long long>(row) * ep.ld_aux_in + col));
+              const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
+                           a3 = unpack_bf16x2(a.w);
+              v[0] *= gelu_erf_grad(a0.x); v[1] *= gelu_erf_grad(a0.y);
+              v[2] *= gelu_erf_grad(a1.x); v[3] *= gelu_erf_grad(a1.y);
+              v[4] *= gelu_erf_grad(a2.x); v[5] *= gelu_erf_grad(a2.y);
+              v[6] *= gelu_erf_grad(a3.x); v[7] *= gelu_erf_grad(a3.y);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= scale;
+            if (ep.residual != nullptr) {
+              const uint4 a = __ldg(
+                  reinterpret_cast<const uint4*>(ep.residual + static_cast<long long>(row) * ep.ld_res + col));
+              const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
+                           a3 = unpack_bf16x2(a.w);
+              v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
+              v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+            }
+            if (ep.out_fp32) {
+              float* o = reinterpret_cast<float*>(ep.out) + static_cast<long long>(row) * ep.ld_out + col;
+              float4 o0, o1;
+              if (ep.accumulate) {
+                o0 = *reinterpret_cast<const float4*>(o);
+                o1 = *reinterpret_cast<const float4*>(o + 4);
+              } else {
+                o0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                o1 = o0;
+              }
+              o0.x += v[0]; o0.y += v[1]; o0.z += v[2]; o0.w += v[3];
+              o1.x += v[4]; o1.y += v[5]; o1.z += v[6]; o1.w += v[7];
+              *reinterpret_cast<float4*>(o) = o0;
+              *reinterpret_cast<float4*>(o + 4) = o1;
+            } else {
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + static_cast<long long>(row) * ep.ld_out +
+                                        col) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                       const GemmEpi& ep, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ma, mb;
+  int rc;
+  if (!A_MN) rc = make_tmap_bf16_2d(&ma, A, M, K, lda, kBM, 64);   // [M][K], box 128 rows x 64 k
+  else       rc = make_tmap_bf16_2d(&ma, A, K, M, lda, kBK, 64);   // [K][M], box 64 k-rows x 64 m
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap_bf16_2d(&mb, B, N, K, ldb, BN, 64);
+  else       rc = make_tmap_bf16_2d(&mb, B, K, N, ldb, kBK, 64);
+  if (rc) return rc;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    OTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, M, N, K, ep);
+  count_launch();
+  OTB_CHECK_CUDA(cudaGetLastError());
+  return OTB_OK;
+}
+
+}  // namespace otb
+
+extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
+                             int M, int N, int K, const otb_gemm_epilogue* e, void* stream) {
+  using namespace otb;
+  OTB_CHECK_ARG(A && B && e && e->out, "otb_gemm_bf16: null pointer");
+  OTB_CHECK_ARG(M > 0 && N > 0 && K > 0, "otb_gemm_bf16: bad shape %d %d %d", M, N, K);
+  OTB_CHECK_ARG(N % 8 == 0, "otb_gemm_bf16: N=%d must be a multiple of 8", N);
+  OTB_CHECK_ARG(e->ld_out % 8 == 0 && e->ld_out >= N, "otb_gemm_bf16: bad ld_out");
+  OTB_CHECK_ARG(!e->accumulate || e->out_fp32, "otb_gemm_bf16: accumulate requires fp32 output");
+  OTB_CHECK_ARG(e->aux_in == nullptr || (e->ld_aux_in % 8 == 0 && e->ld_aux_in >= N), "otb_gemm_bf16: bad ld_aux_in");
+  OTB_CHECK_ARG(e->aux_out == nullptr || (e->ld_aux_out % 8 == 0 && e->ld_aux_out >= N),
+                "otb_gemm_bf16: bad ld_aux_out");
+  OTB_CHECK_ARG(e->residual == nullptr || (e->ld_res % 8 == 0 && e->ld_res >= N), "otb_gemm_bf16: bad ld_res");
+  OTB_CHECK_ARG(e->act >= 0 && e->act <= 2, "otb_gemm_bf16: bad act");
+  if (a_mn_major) OTB_CHECK_ARG(M % 8 == 0 && lda >= M, "otb_gemm_bf16: MN-major A needs M%%8==0, lda>=M");
+  else OTB_CHECK_ARG(lda >= K, "otb_gemm_bf16: lda < K");
+  if (b_mn_major) OTB_CHECK_ARG(ldb >= N, "otb_gemm_bf16: ldb < N");
+  else OTB_CHECK_ARG(ldb >= K, "otb_gemm_bf16: ldb < K");
+
+  GemmEpi ep;
+  ep.bias = e->bias;
+  ep.aux_in = static_cast<const bf16*>(e->aux_in);
+  ep.aux_out = static_cast<bf16*>(e->aux_out);
+  ep.scale_ptr = e->scale_ptr;
+  ep.residual = static_cast<const bf16*>(e->residual);
+  ep.out = e->out;
+  ep.ld_out = e->ld_out; ep.ld_aux_in = e->ld_aux_in; ep.ld_aux_out = e->ld_aux_out; ep.ld_res = e->ld_res;
+  ep.act = e->act; ep.scale_tanh = e->scale_tanh; ep.out_fp32 = e->out_fp32; ep.accumulate = e->accumulate;
+  ep.alpha = e->alpha;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  // Tile-N choice: 256-wide tiles unless that leaves most SMs idle.
+  const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
+  const bool bn128 = (N <= 128) || (tiles256 < sm_count() && N > 128);
+  const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+  if (bn128) {
+    switch (sel) {
+      case 0: return launch_gemm<128, false, false>(A, lda, B, ldb, M, N, K, ep, st);
+      case 1: return launch_gemm<128, false, true>(A, lda, B, ldb, M, N, K, ep, st);
+      case 3: return launch_gemm<128, true, true>(A, lda, B, ldb, M, N, K, ep, st);
+      default: break;
+    }
+  } else {
+    switch (sel) {
+      case 0: return launch_gemm<256, false, false>(A, lda, B, ldb, M, N, K, ep, st);
+      case 1: return launch_gemm<256, false, true>(A, lda, B, ldb, M, N, K, ep, st);
+      case 3: return launch_gemm<256, true, true>(A, lda, B, ldb, M, N, K, ep, st);
+      default: break;
+    }
+  }
+  return set_error(OTB_ERR_UNSUPPORTED, "otb_gemm_bf16: layout (A MN-major, B K-major) not instantiated");
+}

@@ -1,0 +1,35 @@
+// otter_b200 — host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../include/otter_b200.h"
+
+namespace otb {
+
+// thread-local error string behind otb_last_error()
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define OTB_CHECK_ARG(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return otb::set_error(OTB_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define OTB_CHECK_CUDA(expr)                                                                              \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess)                                                                                \
+      return otb::set_error(OTB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                            __LINE__);                                                                    \
+  } while (0)
+
+// Encode a 2D bf16 row-major tensor [rows][cols] (row pitch ld elements) as a TMA tensor map with a
+// SWIZZLE_128B box of box_cols x box_rows (box_cols * 2 bytes must be 128).
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols);
+
+int sm_count();
+
+}  // namespace otb
