@@ -1,0 +1,602 @@
+// otter_b200 — fused attention cores on tcgen05 / TMA (forward + backward).
+//
+// One kernel family serves the three attention cores of the hot path:
+//   (A) perceiver latent x (vision ++ latent) attention      modeling_otter.py:168-179   (two key sources)
+//   (B) gated cross-attention text x latent with media mask   modeling_otter.py:290-333   (text_time mask)
+//   (C) CLIP ViT self-attention (no mask)                     xformers_model/clip.py:112-128
+//
+// Layout: no head permutes — Q/K/V/O are read/written in place inside the projection GEMM outputs
+// ([rows][cols] bf16, head h at columns col0 + h*64), addressed through TMA tensor maps.
+//
+// Forward, per CTA = (128-row query tile, head, problem), 128 threads (thread t owns query row t):
+//   S = Q K^T on tcgen05.mma (128x128x64) into TMEM; rows read back with tcgen05.ld; softmax in fp32
+//   registers (two sweeps over the key tiles: row max, then exp/accumulate — no rescaling of O);
+//   P (bf16) staged in 128B-swizzled smem; O += P V on tcgen05.mma with V consumed MN-major straight
+//   from its TMA tile; O/l written once.  K/V tiles are double-buffered TMA loads.
+// Backward, per CTA = (head, problem): loops key tiles (outer) x query tiles (inner) with
+//   S, dP = dO V^T, dV += P^T dO, dK += dS^T Q, dQ = dS K all on tcgen05 (P/dS staged in smem and
+//   consumed K-major and MN-major from the same bytes); dK/dV accumulate in TMEM across query tiles.
+//
+// Mask semantics of (B) (bit-exact w.r.t. the reference): with tt = text_time[b,row]
+//   tt == 0        -> attention row zeroed after softmax (output row exactly 0, no gradients)
+//   1 <= tt <= T   -> only keys of media slot tt-1 participate
+//   tt > T         -> every key masked with -FLT_MAX => uniform attention 1/(T*n); dS = 0, dV gets dO/(T*n)
+#include "otb_common.cuh"
+#include "otb_host.h"
+
+namespace otb {
+
+constexpr int kAttnThreads = 128;
+constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16 (128 B) = 16 KB
+
+struct AttnParams {
+  int P, H, Sq, Sk1, Sk2;
+  int q_col0, k1_col0, v1_col0, k2_col0, v2_col0;
+  float scale, scale_log2;
+  // forward outputs
+  bf16* out; long long ldo; int o_col0;
+  float* lse;  // [P][H][Sq]
+  // mask (mode B) — text_time == nullptr disables masking
+  const int* text_time; int n_per_media; int T_img;
+  // backward
+  const bf16* o; const bf16* dout; long long ld_do; int do_col0;
+  bf16* dq; long long ld_dq; int dq_col0;
+  bf16* dkv1; long long ld_dkv1; int dk1_col0, dv1_col0;
+  bf16* dkv2; long long ld_dkv2; int dk2_col0, dv2_col0;
+  float* dq_ws;  // [P*Sq][H*64] fp32, only touched when more than one key tile
+};
+
+struct KeyTile {
+  int src, row0, valid, key_base;
+};
+__device__ __forceinline__ KeyTile key_tile(const AttnParams& p, int prob, int j, int nt1) {
+  KeyTile t;
+  if (j < nt1) {
+    t.src = 0; t.row0 = prob * p.Sk1 + j * 128; t.valid = min(128, p.Sk1 - j * 128); t.key_base = j * 128;
+  } else {
+    const int jj = j - nt1;
+    t.src = 1; t.row0 = prob * p.Sk2 + jj * 128; t.valid = min(128, p.Sk2 - jj * 128); t.key_base = p.Sk1 + jj * 128;
+  }
+  return t;
+}
+
+// row class: 0 = zeroed row, 1 = normal, 2 = uniform (fully masked)
+__device__ __forceinline__ int row_class(const AttnParams& p, int tt) {
+  if (p.text_time == nullptr) return 1;
+  if (tt == 0) return 0;
+  return (tt <= p.T_img) ? 1 : 2;
+}
+__device__ __forceinline__ bool key_allowed(const AttnParams& p, int tt, int key_idx) {
+  if (p.text_time == nullptr) return true;
+  return (key_idx / p.n_per_media + 1) == tt;
+}
+
+// write 8 consecutive bf16 (one 16 B unit) of row r, columns [c, c+8) into a [rows][64] SW128 tile chunk
+__device__ __forceinline__ void st_sw128(uint8_t* chunk_base, int r, int c_in_chunk, uint4 v) {
+  const int unit = (c_in_chunk >> 3) ^ (r & 7);
+  *reinterpret_cast<uint4*>(chunk_base + r * 128 + unit * 16) = v;
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+__global__ void __launch_bounds__(kAttnThreads)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv1,
+                const __grid_constant__ CUtensorMap map_kv2, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;                        // 16 KB
+  uint8_t* s_k = s_q + kTileBytes;            // 2 x 16 KB
+  uint8_t* s_v = s_k + 2 * kTileBytes;        // 2 x 16 KB
+  uint8_t* s_p = s_v + 2 * kTileBytes;        // 32 KB: P as two 64-key chunks of [128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kTileBytes);
+  uint64_t* full = bars;        // [2]
+  uint64_t* bar_q = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, prob = blockIdx.z;
+
+  if (tid == 32) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem;         // S: columns [0,128)
+  const uint32_t t_o = tmem + 128;   // O: columns [128,192)
+
+  const int nt1 = (p.Sk1 + 127) / 128, nt2 = (p.Sk2 + 127) / 128, nt = nt1 + nt2;
+  const int nsteps = (nt == 1) ? 1 : 2 * nt;
+
+  const int row = qt * 128 + tid;
+  const bool row_ok = row < p.Sq;
+  int tt = 0;
+  if (p.text_time != nullptr && row_ok) tt = p.text_time[prob * p.Sq + row];
+  const int cls = row_ok ? row_class(p, tt) : 0;
+
+  auto issue_load = [&](int s) {  // thread 0 only
+    const int j = (nt == 1) ? 0 : (s % nt);
+    const bool need_v = (nt == 1) || (s >= nt);
+    const KeyTile kt = key_tile(p, prob, j, nt1);
+    const int st = s & 1;
+    mbar_arrive_expect_tx(&full[st], need_v ? 2 * kTileBytes : kTileBytes);
+    const CUtensorMap* m = kt.src ? &map_kv2 : &map_kv1;
+    tma_load_2d(s_k + st * kTileBytes, m, &full[st], (kt.src ? p.k2_col0 : p.k1_col0) + h * 64, kt.row0);
+    if (need_v) tma_load_2d(s_v + st * kTileBytes, m, &full[st], (kt.src ? p.v2_col0 : p.v1_col0) + h * 64, kt.row0);
+  };
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+  auto issue_s = [&](int st) {  // S = Q K^T
+    const uint64_t da = make_smem_desc(smem_u32(s_q), 16, 1024);
+    const uint64_t db = make_smem_desc(smem_u32(s_k + st * kTileBytes), 16, 1024);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(t_s, da + k * 2, db + k * 2, idesc_s, k != 0);
+  };
+  auto issue_pv = [&](int st, bool accumulate) {  // O += P V   (A = P K-major over keys, B = V MN-major)
+    const uint64_t db = make_smem_desc(smem_u32(s_v + st * kTileBytes), 16, 1024);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint64_t da = make_smem_desc(smem_u32(s_p + (k >> 2) * kTileBytes) + (k & 3) * 32, 16, 1024);
+      umma_bf16(t_o, da, db + k * 128, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+    }
+  };
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_kv1); tma_prefetch_desc(&map_kv2);
+    mbar_arrive_expect_tx(bar_q, kTileBytes);
+    tma_load_2d(s_q, &map_q, bar_q, p.q_col0 + h * 64, prob * p.Sq + qt * 128);
+    issue_load(0);
+    mbar_wait(bar_q, 0);
+    mbar_wait(&full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    umma_commit(bar_s);
+  }
+
+  float m_run = -INFINITY, l_run = 0.f;
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  for (int s = 0; s < nsteps; ++s) {
+    mbar_wait(bar_s, s & 1);
+    if (tid == 0 && s + 1 < nsteps) issue_load(s + 1);
+    tc_fence_after();
+    const int j = (nt == 1) ? 0 : (s % nt);
+    const bool is_p2 = (nt == 1) || (s >= nt);
+    const bool do_max = (nt == 1) || (s < nt);
+    const KeyTile kt = key_tile(p, prob, j, nt1);
+    if (do_max) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        if (cls == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int cc = c * 32 + i;
+            if (cc < kt.valid && key_allowed(p, tt, kt.key_base + cc)) m_run = fmaxf(m_run, __uint_as_float(r[i]));
+          }
+        }
+      }
+    }
+    if (is_p2) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int cc = c * 32 + i;
+          float v = 0.f;
+          if (cc < kt.valid) {
+            if (cls == 1) {
+              if (key_allowed(p, tt, kt.key_base + cc)) v = exp2f((__uint_as_float(r[i]) - m_run) * p.scale_log2);
+            } else if (cls == 2) {
+              v = 1.0f;
+            }
+          }
+          pv[i] = v;
+          l_run += v;
+        }
+        uint8_t* chunk = s_p + (c >> 1) * kTileBytes;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]); o.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
+          o.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]); o.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
+          st_sw128(chunk, tid, (c & 1) * 32 + g * 8, o);
+        }
+      }
+      fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      if (is_p2) issue_pv(s & 1, (nt != 1) && (s > nt));
+      if (s + 1 < nsteps) {
+        mbar_wait(&full[(s + 1) & 1], ((s + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_s((s + 1) & 1);
+      }
+      umma_commit(bar_s);
+    }
+  }
+  mbar_wait(bar_s, nsteps & 1);
+  tc_fence_after();
+
+  // ---- epilogue: O / l -> bf16, LSE ----
+  const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_o + lane_addr + c * 32, r);
+    tmem_ld_wait();
+    if (row_ok) {
+      bf16* dst = p.out + static_cast<long long>(prob * p.Sq + row) * p.ldo + p.o_col0 + h * 64 + c * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
+        o.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
+        o.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
+        o.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(dst + g * 8) = o;
+      }
+    }
+  }
+  if (row_ok && p.lse != nullptr) {
+    p.lse[(static_cast<long long>(prob) * p.H + h) * p.Sq + row] =
+        (cls == 1 && l_run > 0.f) ? (m_run * p.scale + logf(l_run)) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+__global__ void __launch_bounds__(kAttnThreads)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                const __grid_constant__ CUtensorMap map_kv1, const __grid_constant__ CUtensorMap map_kv2,
+                AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_k = smem;                      // 16 KB  K_j  [128 keys][64 d]
+  uint8_t* s_v = s_k + kTileBytes;          // 16 KB  V_j
+  uint8_t* s_q = s_v + kTileBytes;          // 16 KB  Q_i  [128 rows][64 d]
+  uint8_t* s_do = s_q + kTileBytes;         // 16 KB  dO_i
+  uint8_t* s_p = s_do + kTileBytes;         // 32 KB  P   [128 rows][128 keys] (2 chunks)
+  uint8_t* s_ds = s_p + 2 * kTileBytes;     // 32 KB  dS * scale
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ds + 2 * kTileBytes);
+  uint64_t* bar_kv = bars;
+  uint64_t* bar_qdo = bars + 1;
+  uint64_t* bar_mma = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, prob = blockIdx.y;
+
+  if (tid == 32) {
+    mbar_init(bar_kv, 1); mbar_init(bar_qdo, 1); mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_dp = tmem + 128, t_dv = tmem + 256, t_dk = tmem + 320, t_dq = tmem + 384;
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+
+  const int nt1 = (p.Sk1 + 127) / 128, nt2 = (p.Sk2 + 127) / 128, nkt = nt1 + nt2;
+  const int nqt = (p.Sq + 127) / 128;
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);   // S, dP
+  constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);      // dV = P^T dO, dK = dS^T Q
+  constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);    // dQ = dS K
+
+  uint32_t ph_kv = 0, ph_qdo = 0, ph_mma = 0;
+  if (tid == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_kv1); tma_prefetch_desc(&map_kv2);
+  }
+
+  for (int j = 0; j < nkt; ++j) {
+    const KeyTile kt = key_tile(p, prob, j, nt1);
+    if (tid == 0) {
+      const CUtensorMap* m = kt.src ? &map_kv2 : &map_kv1;
+      mbar_arrive_expect_tx(bar_kv, 2 * kTileBytes);
+      tma_load_2d(s_k, m, bar_kv, (kt.src ? p.k2_col0 : p.k1_col0) + h * 64, kt.row0);
+      tma_load_2d(s_v, m, bar_kv, (kt.src ? p.v2_col0 : p.v1_col0) + h * 64, kt.row0);
+    }
+    for (int i = 0; i < nqt; ++i) {
+      const int row = i * 128 + tid;
+      const bool row_ok = row < p.Sq;
+      const long long grow = static_cast<long long>(prob) * p.Sq + row;
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bar_qdo, 2 * kTileBytes);
+        tma_load_2d(s_q, &map_q, bar_qdo, p.q_col0 + h * 64, prob * p.Sq + i * 128);
+        tma_load_2d(s_do, &map_do, bar_qdo, p.do_col0 + h * 64, prob * p.Sq + i * 128);
+      }
+      // per-row scalars (overlaps the TMA): delta = rowsum(dO . O), lse, class
+      int tt = 0;
+      float delta = 0.f, lse = 0.f;
+      if (row_ok) {
+        if (p.text_time != nullptr) tt = p.text_time[grow];
+        const uint4* po = reinterpret_cast<const uint4*>(p.o + grow * p.ldo + p.o_col0 + h * 64);
+        const uint4* pd = reinterpret_cast<const uint4*>(p.dout + grow * p.ld_do + p.do_col0 + h * 64);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint4 a = __ldg(po + g), b = __ldg(pd + g);
+          const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+          const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+          delta += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x +
+                   a3.y * b3.y;
+        }
+        lse = p.lse[(static_cast<long long>(prob) * p.H + h) * p.Sq + row];
+      }
+      const int cls = row_ok ? row_class(p, tt) : 0;
+      const float inv_cnt = 1.0f / static_cast<float>(p.Sk1 + p.Sk2);
+
+      if (tid == 0) {
+        if (i == 0) { mbar_wait(bar_kv, ph_kv); }
+        mbar_wait(bar_qdo, ph_qdo);
+        tc_fence_after();
+        const uint64_t dq_ = make_smem_desc(smem_u32(s_q), 16, 1024);
+        const uint64_t dk_ = make_smem_desc(smem_u32(s_k), 16, 1024);
+        const uint64_t ddo = make_smem_desc(smem_u32(s_do), 16, 1024);
+        const uint64_t dv_ = make_smem_desc(smem_u32(s_v), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(t_s, dq_ + k * 2, dk_ + k * 2, idesc_s, k != 0);      // S = Q K^T
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(t_dp, ddo + k * 2, dv_ + k * 2, idesc_s, k != 0);    // dP = dO V^T
+        umma_commit(bar_mma);
+      }
+      ph_qdo ^= 1;
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rp[32];
+        tmem_ld32(t_s + lane_addr + c * 32, rs);
+        tmem_ld32(t_dp + lane_addr + c * 32, rp);
+        tmem_ld_wait();
+        uint8_t* pchunk = s_p + (c >> 1) * kTileBytes;
+        uint8_t* dchunk = s_ds + (c >> 1) * kTileBytes;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8], dv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int cc = c * 32 + g * 8 + e;
+            float pr = 0.f, ds = 0.f;
+            if (cc < kt.valid) {
+              if (cls == 1) {
+                if (key_allowed(p, tt, kt.key_base + cc)) {
+                  pr = __expf(__uint_as_float(rs[g * 8 + e]) * p.scale - lse);
+                  ds = pr * (__uint_as_float(rp[g * 8 + e]) - delta) * p.scale;
+                }
+              } else if (cls == 2) {
+                pr = inv_cnt;
+              }
+            }
+            pv[e] = pr; dv[e] = ds;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(pv[0], pv[1]); o.y = pack_bf16x2(pv[2], pv[3]);
+          o.z = pack_bf16x2(pv[4], pv[5]); o.w = pack_bf16x2(pv[6], pv[7]);
+          st_sw128(pchunk, tid, (c & 1) * 32 + g * 8, o);
+          o.x = pack_bf16x2(dv[0], dv[1]); o.y = pack_bf16x2(dv[2], dv[3]);
+          o.z = pack_bf16x2(dv[4], dv[5]); o.w = pack_bf16x2(dv[6], dv[7]);
+          st_sw128(dchunk, tid, (c & 1) * 32 + g * 8, o);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t acc = (i > 0) ? 1u : 0u;
+        // dV += P^T dO ; dK += dS^T Q      A MN-major: 2 chunks of 64 keys, LBO = chunk stride, k-step = 16 q rows
+        const uint64_t a_p = make_smem_desc(smem_u32(s_p), kTileBytes, 1024);
+        const uint64_t a_ds = make_smem_desc(smem_u32(s_ds), kTileBytes, 1024);
+        const uint64_t b_do = make_smem_desc(smem_u32(s_do), 16, 1024);
+        const uint64_t b_q = make_smem_desc(smem_u32(s_q), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16(t_dv, a_p + k * 128, b_do + k * 128, idesc_t, (acc || k != 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16(t_dk, a_ds + k * 128, b_q + k * 128, idesc_t, (acc || k != 0) ? 1u : 0u);
+        // dQ = dS K   A K-major over keys (2 chunks), B = K_j MN-major
+        const uint64_t b_k = make_smem_desc(smem_u32(s_k), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t a = make_smem_desc(smem_u32(s_ds + (k >> 2) * kTileBytes) + (k & 3) * 32, 16, 1024);
+          umma_bf16(t_dq, a, b_k + k * 128, idesc_dq, k != 0);
+        }
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after();
+
+      // dQ tile: accumulate across key tiles through the fp32 workspace (same thread owns the same row)
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_dq + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+          float* ws = (nkt > 1) ? p.dq_ws + grow * (p.H * 64) + h * 64 + c * 32 : nullptr;
+          if (j > 0) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(ws + e);
+              v[e] += w.x; v[e + 1] += w.y; v[e + 2] += w.z; v[e + 3] += w.w;
+            }
+          }
+          if (j == nkt - 1) {
+            bf16* dst = p.dq + grow * p.ld_dq + p.dq_col0 + h * 64 + c * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o;
+              o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]); o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+              o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]); o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(dst + g * 8) = o;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              *reinterpret_cast<float4*>(ws + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+    ph_kv ^= 1;
+
+    // dV_j, dK_j complete: TMEM lane t = key t of this tile
+    {
+      const bool key_ok = tid < kt.valid;
+      bf16* base = kt.src ? p.dkv2 : p.dkv1;
+      const long long ld = kt.src ? p.ld_dkv2 : p.ld_dkv1;
+      const int dkc = kt.src ? p.dk2_col0 : p.dk1_col0, dvc = kt.src ? p.dv2_col0 : p.dv1_col0;
+#pragma unroll 1
+      for (int w = 0; w < 2; ++w) {      // 0: dV, 1: dK
+        const uint32_t t_src = w ? t_dk : t_dv;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_src + lane_addr + c * 32, r);
+          tmem_ld_wait();
+          if (key_ok) {
+            bf16* dst = base + static_cast<long long>(kt.row0 + tid) * ld + (w ? dkc : dvc) + h * 64 + c * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
+              o.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
+              o.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
+              o.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+              *reinterpret_cast<uint4*>(dst + g * 8) = o;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+constexpr int kAttnFwdSmem = 7 * kTileBytes + 1024 + 128;
+constexpr int kAttnBwdSmem = 8 * kTileBytes + 1024 + 128;
+
+}  // namespace otb
+
+using namespace otb;
+
+static int check_common(const otb_attn_desc* d) {
+  OTB_CHECK_ARG(d != nullptr, "otb_attn: null descriptor");
+  OTB_CHECK_ARG(d->P > 0 && d->H > 0 && d->Sq > 0 && d->Sk1 > 0 && d->Sk2 >= 0, "otb_attn: bad sizes");
+  OTB_CHECK_ARG(d->head_dim == 64, "otb_attn: head_dim must be 64 (Otter/CLIP-L: 64)");
+  OTB_CHECK_ARG(d->q && d->kv1 && (d->Sk2 == 0 || d->kv2), "otb_attn: null tensor");
+  OTB_CHECK_ARG(d->text_time == nullptr || (d->Sk2 == 0 && d->n_per_media > 0 && d->T_img * d->n_per_media == d->Sk1),
+                "otb_attn: media mask needs a single key source with Sk1 == T_img * n_per_media");
+  return OTB_OK;
+}
+
+static void fill_params(const otb_attn_desc* d, AttnParams& p) {
+  p.P = d->P; p.H = d->H; p.Sq = d->Sq; p.Sk1 = d->Sk1; p.Sk2 = d->Sk2;
+  p.q_col0 = d->q_col0; p.k1_col0 = d->k1_col0; p.v1_col0 = d->v1_col0; p.k2_col0 = d->k2_col0; p.v2_col0 = d->v2_col0;
+  p.scale = d->scale; p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.out = static_cast<bf16*>(d->out); p.ldo = d->ld_out; p.o_col0 = d->out_col0;
+  p.lse = d->lse;
+  p.text_time = d->text_time; p.n_per_media = d->n_per_media; p.T_img = d->T_img;
+  p.o = static_cast<const bf16*>(d->out);
+  p.dout = nullptr; p.dq = nullptr; p.dkv1 = nullptr; p.dkv2 = nullptr; p.dq_ws = nullptr;
+  p.ld_do = p.ld_dq = p.ld_dkv1 = p.ld_dkv2 = 0;
+  p.do_col0 = p.dq_col0 = p.dk1_col0 = p.dv1_col0 = p.dk2_col0 = p.dv2_col0 = 0;
+}
+
+extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
+  int rc = check_common(d);
+  if (rc) return rc;
+  OTB_CHECK_ARG(d->out != nullptr, "otb_attn_fwd: null out");
+  AttnParams p;
+  fill_params(d, p);
+  CUtensorMap mq, mk1, mk2;
+  rc = make_tmap_bf16_2d(&mq, d->q, (uint64_t)d->P * d->Sq, d->q_cols, d->ldq, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&mk1, d->kv1, (uint64_t)d->P * d->Sk1, d->kv1_cols, d->ldkv1, 128, 64);
+  if (rc) return rc;
+  if (d->Sk2 > 0) rc = make_tmap_bf16_2d(&mk2, d->kv2, (uint64_t)d->P * d->Sk2, d->kv2_cols, d->ldkv2, 128, 64);
+  else mk2 = mk1;
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    OTB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwdSmem));
+    attr = true;
+  }
+  dim3 grid((d->Sq + 127) / 128, d->H, d->P);
+  attn_fwd_kernel<<<grid, kAttnThreads, kAttnFwdSmem, static_cast<cudaStream_t>(stream)>>>(mq, mk1, mk2, p);
+  count_launch();
+  OTB_CHECK_CUDA(cudaGetLastError());
+  return OTB_OK;
+}
+
+extern "C" int otb_attn_bwd(const otb_attn_desc* d, const otb_attn_grads* g, void* stream) {
+  int rc = check_common(d);
+  if (rc) return rc;
+  OTB_CHECK_ARG(g && d->out && d->lse && g->dout && g->dq && g->dkv1 && (d->Sk2 == 0 || g->dkv2),
+                "otb_attn_bwd: null tensor");
+  const int nkt = (d->Sk1 + 127) / 128 + (d->Sk2 + 127) / 128;
+  OTB_CHECK_ARG(nkt == 1 || g->dq_ws != nullptr, "otb_attn_bwd: dq workspace required for >1 key tile");
+  AttnParams p;
+  fill_params(d, p);
+  p.dout = static_cast<const bf16*>(g->dout); p.ld_do = g->ld_dout; p.do_col0 = g->dout_col0;
+  p.dq = static_cast<bf16*>(g->dq); p.ld_dq = g->ld_dq; p.dq_col0 = g->dq_col0;
+  p.dkv1 = static_cast<bf16*>(g->dkv1); p.ld_dkv1 = g->ld_dkv1; p.dk1_col0 = g->dk1_col0; p.dv1_col0 = g->dv1_col0;
+  p.dkv2 = static_cast<bf16*>(g->dkv2); p.ld_dkv2 = g->ld_dkv2; p.dk2_col0 = g->dk2_col0; p.dv2_col0 = g->dv2_col0;
+  p.dq_ws = g->dq_ws;
+  CUtensorMap mq, mdo, mk1, mk2;
+  rc = make_tmap_bf16_2d(&mq, d->q, (uint64_t)d->P * d->Sq, d->q_cols, d->ldq, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&mdo, g->dout, (uint64_t)d->P * d->Sq, g->dout_cols, g->ld_dout, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&mk1, d->kv1, (uint64_t)d->P * d->Sk1, d->kv1_cols, d->ldkv1, 128, 64);
+  if (rc) return rc;
+  if (d->Sk2 > 0) rc = make_tmap_bf16_2d(&mk2, d->kv2, (uint64_t)d->P * d->Sk2, d->kv2_cols, d->ldkv2, 128, 64);
+  else mk2 = mk1;
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    OTB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
+    attr = true;
+  }
+  dim3 grid(d->H, d->P);
+  attn_bwd_kernel<<<grid, kAttnThreads, kAttnBwdSmem, static_cast<cudaStream_t>(stream)>>>(mq, mdo, mk1, mk2, p);
+  count_launch();
+  OTB_CHECK_CUDA(cudaGetLastError());
+  return OTB_OK;
+}

@@ -76,6 +76,106 @@ typedef struct otb_gemm_epilogue {
 int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb, int M,
                   int N, int K, const otb_gemm_epilogue* epi, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused attention cores (tcgen05 QK^T / PV, online fp32 softmax, TMA-staged K/V tiles).
+ *   (A) perceiver  latent x (vision ++ latents)   modeling_otter.py:168-179  (Sk2 > 0: second key source)
+ *   (B) gated x-attn text x latents, media mask   modeling_otter.py:290-333  (text_time != NULL)
+ *   (C) CLIP self-attention                       xformers_model/clip.py:112-128
+ * Tensors are addressed in place inside the projection outputs: a matrix is [P*S rows][cols] bf16
+ * with row pitch ld; head h lives at columns col0 + h*64.  `*_cols` is the logical column count of the
+ * matrix (TMA bound).  Problem p uses rows [p*S, (p+1)*S).  head_dim must be 64.
+ *   out[p*Sq+i, out_col0+h*64+d] = sum_j softmax_j(scale * q_i.k_j + mask) v_j[d]
+ *   lse [P][H][Sq] fp32 (may be NULL for inference) is what the backward needs.
+ * Mask (B): text_time int32 [P][Sq] from otb_text_time(); key j belongs to media slot j / n_per_media.
+ *   tt==0 -> row zeroed; 1<=tt<=T_img -> only slot tt-1; tt>T_img -> uniform over all keys.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct otb_attn_desc {
+  const void* q;
+  const void* kv1;
+  const void* kv2; /* optional second key/value source (perceiver latents), NULL if Sk2 == 0 */
+  void* out;
+  float* lse;
+  const int32_t* text_time;
+  int64_t ldq, ldkv1, ldkv2, ld_out;
+  int32_t q_cols, kv1_cols, kv2_cols;
+  int32_t q_col0, k1_col0, v1_col0, k2_col0, v2_col0, out_col0;
+  int32_t n_per_media, T_img;
+  int32_t P, H, Sq, Sk1, Sk2, head_dim;
+  float scale;
+} otb_attn_desc;
+
+typedef struct otb_attn_grads {
+  const void* dout; /* [P*Sq][..] bf16, same head layout as out */
+  void* dq;         /* [P*Sq][..] bf16 */
+  void* dkv1;       /* [P*Sk1][..] bf16 : dK at dk1_col0 + h*64, dV at dv1_col0 + h*64 */
+  void* dkv2;       /* [P*Sk2][..] bf16 or NULL */
+  float* dq_ws;     /* fp32 [P*Sq][H*64] scratch, required when the keys span more than one 128-key tile */
+  int64_t ld_dout, ld_dq, ld_dkv1, ld_dkv2;
+  int32_t dout_cols, dout_col0, dq_col0, dk1_col0, dv1_col0, dk2_col0, dv2_col0;
+  int32_t _pad;
+} otb_attn_grads;
+
+int otb_attn_fwd(const otb_attn_desc* d, void* stream);
+int otb_attn_bwd(const otb_attn_desc* d, const otb_attn_grads* g, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Index / mask construction (integer, bit-exact):  modeling_otter.py:296-311
+ *   text_time[b,i] = cumsum(media_locations[b,:])[i]; if !attend_previous: +1 on non-media tokens,
+ *   then entries > count_nonzero(media_locations[b]) wrap to 0.
+ * ------------------------------------------------------------------------------------------- */
+int otb_text_time(const uint8_t* media_locations, int B, int L, int attend_previous, int32_t* text_time,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm (eps, affine; fp32 statistics)  nn.LayerNorm on the path: modeling_otter.py:136-137,144,
+ * 208,251,364; clip.py:160,162,404.  x,y bf16 [rows][D]; gamma/beta fp32 [D]; mean/rstd fp32 [rows].
+ * Backward: dx (+ optional `add`, the residual-branch gradient, fused) and per-column parameter
+ * gradients via a deterministic two-stage reduction (ws: fp32 [2][chunks][D], chunks = otb_ln_chunks()).
+ * ------------------------------------------------------------------------------------------- */
+int otb_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
+                      float* mean, float* rstd, int rows, int D, float eps, void* stream);
+int otb_ln_chunks(int rows, int D);
+int otb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean,
+                      const float* rstd, const float* gamma, const void* add, int64_t ldadd, void* dx,
+                      int64_t lddx, float* dgamma, float* dbeta, int accumulate, float* ws, int rows, int D,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small HBM-bound passes around the GEMMs.
+ * ------------------------------------------------------------------------------------------- */
+/* dst(bf16)[i] = src(fp32)[i]  — bf16 shadow of fp32 master weights (autocast-equivalent). */
+int otb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int otb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+/* out[r,:] = bf16(src[(r / div) % mod, :])  fp32 [mod][D] -> bf16 [rows][D]; latents repeat (:232). */
+int otb_bcast_rows(const float* src, int div, int mod, void* out, int rows, int D, void* stream);
+/* out[g,:] (+)= sum_{r : (r/div)%mod == g} x[r,:]   bf16 [rows][D] -> fp32 [mod][D]
+ * (gradient of latents repeat (:232) and of the frame_embs broadcast (:224-226)). Deterministic. */
+int otb_grouped_colsum(const void* x, int64_t ldx, int rows, int D, int div, int mod, float* out, int accumulate,
+                       void* stream);
+/* Tanh-gate gradient (modeling_otter.py:387-388,393):  *dgate (+)= (1 - tanh(*gate)^2) * sum(dy . a)
+ * dy, a bf16 [n]; ws fp32 [otb_dot_blocks()] scratch. Deterministic two-stage reduction. */
+int otb_dot_blocks(void);
+int otb_gate_grad(const void* dy, const void* a, int64_t n, const float* gate, float* dgate, int accumulate,
+                  float* ws, void* stream);
+/* loss = mean(x^2) (fp32, *loss written), dx = 2 x / n  — the M1 harness loss. */
+int otb_sqmean_loss(const void* x, int64_t n, float* loss, void* dx, float* ws, void* stream);
+
+/* CLIP embeddings (xformers_model/clip.py:73-81): */
+/* im2col of non-overlapping patches: pixels [N][3][H][W] (fp32 if pix_fp32 else bf16) ->
+ * out bf16 [N*(H/p)*(W/p)][Kpad], column c*p*p + i*p + j, zero padded to Kpad. */
+int otb_im2col_patches(const void* pixels, int pix_fp32, int N, int H, int W, int patch, void* out, int Kpad,
+                       void* stream);
+/* h[n,0,:] = cls + pos[0]; h[n,1+t,:] = patch[n*np+t,:] + pos[1+t]   -> bf16 [N][np+1][D] */
+int otb_clip_assemble(const void* patch_emb, const float* cls, const float* pos, void* out, int N, int np, int D,
+                      void* stream);
+/* media[img*v + t, :] = hidden[img, 1+t, :] (+ frame_embs[img % F])  (modeling_otter.py:991,224-227) */
+int otb_media_from_clip(const void* hidden, const float* frame_embs, int F, void* out, int n_img, int v, int D,
+                        void* stream);
+/* Fuyu patch scatter (fuyu/modeling_fuyu.py:65-77): for s with idx[b,s] >= 0:
+ * out[b,s,:] = cont[b_off[b] + idx[b,s], :] ; else out[b,s,:] = word[b,s,:]. bf16, D % 8 == 0. */
+int otb_fuyu_scatter(const void* word, const void* cont, const int64_t* idx, const int64_t* b_off, void* out,
+                     int B, int S, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

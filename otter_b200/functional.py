@@ -1,0 +1,324 @@
+"""Thin torch-tensor wrappers over the C ABI (include/otter_b200.h).
+
+PyTorch is plumbing only here: it owns device memory and the current CUDA stream; every arithmetic
+operation on the hot path is a kernel of libotter_b200.so.  All activations are bf16, row-major with
+unit column stride (row pitch may exceed the logical width so column slices work in place).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AttnDesc, AttnGrads, GemmEpilogue, check
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _req(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.OtbError(f"{name} must be a CUDA tensor (otter_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.OtbError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() >= 1 and t.stride(-1) != 1:
+        raise _lib.OtbError(f"{name} must have unit stride in its last dim")
+    return t
+
+
+def _mat(t, name="matrix"):
+    """2-D view [rows, cols] with unit column stride (leading dims flattened when contiguous)."""
+    _req(t, BF16, name)
+    if t.dim() == 2:
+        return t
+    return t.reshape(-1, t.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+def _gemm_raw(A, a_mn, lda, B, b_mn, ldb, M, N, K, out, *, bias=None, act=0, aux_out=None, aux_in=None,
+              scale_ptr=None, scale_tanh=False, alpha=1.0, residual=None, accumulate=False):
+    lib = _lib.load()
+    e = GemmEpilogue()
+    e.bias = _p(bias)
+    e.aux_in = _p(aux_in)
+    e.aux_out = _p(aux_out)
+    e.scale_ptr = _p(scale_ptr)
+    e.residual = _p(residual)
+    e.out = _p(out)
+    e.ld_out = out.stride(0)
+    e.ld_aux_in = aux_in.stride(0) if aux_in is not None else 0
+    e.ld_aux_out = aux_out.stride(0) if aux_out is not None else 0
+    e.ld_res = residual.stride(0) if residual is not None else 0
+    e.act = act
+    e.scale_tanh = 1 if scale_tanh else 0
+    e.out_fp32 = 1 if out.dtype == torch.float32 else 0
+    e.accumulate = 1 if accumulate else 0
+    e.alpha = alpha
+    check(lib.otb_gemm_bf16(_p(A), int(a_mn), lda, _p(B), int(b_mn), ldb, M, N, K, C.byref(e), _stream()),
+          "otb_gemm_bf16")
+    return out
+
+
+def linear_fwd(x, w, *, out=None, out_dtype=BF16, **epi):
+    """y[M,N] = epilogue(x[M,K] @ w[N,K]^T)   (nn.Linear forward)."""
+    x, w = _mat(x, "x"), _mat(w, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (x.shape, w.shape)
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=out_dtype)
+    if epi.get("bias") is not None:
+        _req(epi["bias"], torch.float32, "bias")
+    return _gemm_raw(x, 0, x.stride(0), w, 0, w.stride(0), M, N, K, out, **epi)
+
+
+def linear_dgrad(dy, w, *, out=None, out_dtype=BF16, **epi):
+    """dx[M,K] = epilogue(dy[M,N] @ w[N,K])   — w is consumed MN-major in place (no transpose copy)."""
+    dy, w = _mat(dy, "dy"), _mat(w, "w")
+    M, N = dy.shape
+    K = w.shape[1]
+    assert w.shape[0] == N, (dy.shape, w.shape)
+    if out is None:
+        out = torch.empty((M, K), device=dy.device, dtype=out_dtype)
+    return _gemm_raw(dy, 0, dy.stride(0), w, 1, w.stride(0), M, K, N, out, **epi)
+
+
+def linear_wgrad(dy, x, *, out=None, accumulate=False, **epi):
+    """dW[N,K] (fp32) (+)= dy[M,N]^T @ x[M,K]   — both operands consumed MN-major in place."""
+    dy, x = _mat(dy, "dy"), _mat(x, "x")
+    M, N = dy.shape
+    K = x.shape[1]
+    assert x.shape[0] == M, (dy.shape, x.shape)
+    if out is None:
+        out = torch.empty((N, K), device=dy.device, dtype=torch.float32)
+        accumulate = False
+    return _gemm_raw(dy, 1, dy.stride(0), x, 1, x.stride(0), N, K, M, out, accumulate=accumulate, **epi)
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps=1e-5, want_stats=True):
+    x2 = _mat(x, "x")
+    _req(gamma, torch.float32, "gamma"), _req(beta, torch.float32, "beta")
+    rows, D = x2.shape
+    y = torch.empty((rows, D), device=x.device, dtype=BF16)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    check(_lib.load().otb_layernorm_fwd(_p(x2), x2.stride(0), _p(gamma), _p(beta), _p(y), y.stride(0), _p(mean),
+                                        _p(rstd), rows, D, eps, _stream()), "otb_layernorm_fwd")
+    return y.view(x.shape), mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, add=None, want_dx=True, dgamma=None, dbeta=None, accumulate=False,
+                  want_param_grads=True):
+    """Returns (dx or None, dgamma, dbeta). `add` (bf16, same shape) is summed into dx (fused residual grad)."""
+    lib = _lib.load()
+    dy2, x2 = _mat(dy, "dy"), _mat(x, "x")
+    rows, D = x2.shape
+    dx = torch.empty((rows, D), device=x.device, dtype=BF16) if want_dx else None
+    add2 = _mat(add, "add") if add is not None else None
+    ws = None
+    if want_param_grads:
+        if dgamma is None:
+            dgamma = torch.empty(D, device=x.device, dtype=torch.float32)
+            dbeta = torch.empty(D, device=x.device, dtype=torch.float32)
+            accumulate = False
+        ws = torch.empty(2 * lib.otb_ln_chunks(rows, D) * D, device=x.device, dtype=torch.float32)
+    else:
+        dgamma = dbeta = None
+    check(lib.otb_layernorm_bwd(_p(dy2), dy2.stride(0), _p(x2), x2.stride(0), _p(mean), _p(rstd), _p(gamma),
+                                _p(add2), add2.stride(0) if add2 is not None else 0, _p(dx),
+                                dx.stride(0) if dx is not None else 0, _p(dgamma), _p(dbeta), int(accumulate), _p(ws),
+                                rows, D, _stream()), "otb_layernorm_bwd")
+    return (dx.view(x.shape) if dx is not None else None), dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+class AttnSpec:
+    """Where Q / K / V / O live inside their 2-D buffers (see otb_attn_desc)."""
+
+    def __init__(self, q, q_col0, kv1, k1_col0, v1_col0, P, H, Sq, Sk1, scale, kv2=None, k2_col0=0, v2_col0=0, Sk2=0,
+                 text_time=None, n_per_media=0, T_img=0):
+        self.q, self.q_col0 = _mat(q, "q"), q_col0
+        self.kv1, self.k1_col0, self.v1_col0 = _mat(kv1, "kv1"), k1_col0, v1_col0
+        self.kv2 = _mat(kv2, "kv2") if kv2 is not None else None
+        self.k2_col0, self.v2_col0 = k2_col0, v2_col0
+        self.P, self.H, self.Sq, self.Sk1, self.Sk2, self.scale = P, H, Sq, Sk1, Sk2, scale
+        self.text_time, self.n_per_media, self.T_img = text_time, n_per_media, T_img
+        assert self.q.shape[0] == P * Sq and self.kv1.shape[0] == P * Sk1
+        if text_time is not None:
+            _req(text_time, torch.int32, "text_time")
+            assert text_time.numel() == P * Sq
+
+    def desc(self, out, out_col0, lse):
+        d = AttnDesc()
+        d.q, d.kv1, d.kv2, d.out, d.lse = _p(self.q), _p(self.kv1), _p(self.kv2), _p(out), _p(lse)
+        d.text_time = _p(self.text_time)
+        d.ldq, d.ldkv1 = self.q.stride(0), self.kv1.stride(0)
+        d.ldkv2 = self.kv2.stride(0) if self.kv2 is not None else 0
+        d.ld_out = out.stride(0)
+        d.q_cols, d.kv1_cols = self.q.shape[1], self.kv1.shape[1]
+        d.kv2_cols = self.kv2.shape[1] if self.kv2 is not None else 0
+        d.q_col0, d.k1_col0, d.v1_col0 = self.q_col0, self.k1_col0, self.v1_col0
+        d.k2_col0, d.v2_col0, d.out_col0 = self.k2_col0, self.v2_col0, out_col0
+        d.n_per_media, d.T_img = self.n_per_media, self.T_img
+        d.P, d.H, d.Sq, d.Sk1, d.Sk2, d.head_dim = self.P, self.H, self.Sq, self.Sk1, self.Sk2, 64
+        d.scale = self.scale
+        return d
+
+
+def attn_fwd(spec, out=None, out_col0=0, want_lse=True):
+    if out is None:
+        out = torch.empty((spec.P * spec.Sq, spec.H * 64), device=spec.q.device, dtype=BF16)
+    lse = torch.empty((spec.P, spec.H, spec.Sq), device=spec.q.device, dtype=torch.float32) if want_lse else None
+    d = spec.desc(out, out_col0, lse)
+    check(_lib.load().otb_attn_fwd(C.byref(d), _stream()), "otb_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(spec, out, out_col0, lse, dout, dout_col0, dq, dq_col0, dkv1, dk1_col0, dv1_col0, dkv2=None, dk2_col0=0,
+             dv2_col0=0):
+    d = spec.desc(out, out_col0, lse)
+    g = AttnGrads()
+    dout = _mat(dout, "dout")
+    g.dout, g.dq, g.dkv1, g.dkv2 = _p(dout), _p(dq), _p(dkv1), _p(dkv2)
+    nkt = (spec.Sk1 + 127) // 128 + (spec.Sk2 + 127) // 128
+    ws = torch.empty((spec.P * spec.Sq, spec.H * 64), device=dout.device, dtype=torch.float32) if nkt > 1 else None
+    g.dq_ws = _p(ws)
+    g.ld_dout, g.ld_dq, g.ld_dkv1 = dout.stride(0), dq.stride(0), dkv1.stride(0)
+    g.ld_dkv2 = dkv2.stride(0) if dkv2 is not None else 0
+    g.dout_cols, g.dout_col0, g.dq_col0 = dout.shape[1], dout_col0, dq_col0
+    g.dk1_col0, g.dv1_col0, g.dk2_col0, g.dv2_col0 = dk1_col0, dv1_col0, dk2_col0, dv2_col0
+    check(_lib.load().otb_attn_bwd(C.byref(d), C.byref(g), _stream()), "otb_attn_bwd")
+    return dq, dkv1, dkv2
+
+
+def text_time(media_locations, attend_previous=True):
+    """bool/uint8 [B,L] -> int32 [B,L]  (bit-exact restatement of modeling_otter.py:298-311)."""
+    ml = media_locations
+    if ml.dtype == torch.bool:
+        ml = ml.view(torch.uint8) if ml.is_contiguous() else ml.contiguous().view(torch.uint8)
+    _req(ml, torch.uint8, "media_locations")
+    ml = ml.contiguous()
+    B, L = ml.shape
+    out = torch.empty((B, L), device=ml.device, dtype=torch.int32)
+    check(_lib.load().otb_text_time(_p(ml), B, L, int(bool(attend_previous)), _p(out), _stream()), "otb_text_time")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# small passes
+# ------------------------------------------------------------------------------------------------
+def cast_bf16(src, out=None):
+    _req(src, torch.float32, "src")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=BF16)
+    check(_lib.load().otb_cast_f32_bf16(_p(src), _p(out), src.numel(), _stream()), "otb_cast_f32_bf16")
+    return out
+
+
+def cast_f32(src, out=None):
+    _req(src, BF16, "src")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    check(_lib.load().otb_cast_bf16_f32(_p(src), _p(out), src.numel(), _stream()), "otb_cast_bf16_f32")
+    return out
+
+
+def bcast_rows(src, rows, div, mod):
+    _req(src, torch.float32, "src")
+    D = src.shape[-1]
+    out = torch.empty((rows, D), device=src.device, dtype=BF16)
+    check(_lib.load().otb_bcast_rows(_p(src), div, mod, _p(out), rows, D, _stream()), "otb_bcast_rows")
+    return out
+
+
+def grouped_colsum(x, div, mod, out=None, accumulate=False):
+    x2 = _mat(x, "x")
+    rows, D = x2.shape
+    if out is None:
+        out = torch.empty((mod, D), device=x.device, dtype=torch.float32)
+        accumulate = False
+    check(_lib.load().otb_grouped_colsum(_p(x2), x2.stride(0), rows, D, div, mod, _p(out), int(accumulate), _stream()),
+          "otb_grouped_colsum")
+    return out
+
+
+def gate_grad(dy, a, gate, dgate=None, accumulate=False):
+    lib = _lib.load()
+    _req(dy, BF16, "dy"), _req(a, BF16, "a"), _req(gate, torch.float32, "gate")
+    assert dy.is_contiguous() and a.is_contiguous() and dy.numel() == a.numel()
+    if dgate is None:
+        dgate = torch.empty(1, device=dy.device, dtype=torch.float32)
+        accumulate = False
+    ws = torch.empty(lib.otb_dot_blocks(), device=dy.device, dtype=torch.float32)
+    check(lib.otb_gate_grad(_p(dy), _p(a), dy.numel(), _p(gate), _p(dgate), int(accumulate), _p(ws), _stream()),
+          "otb_gate_grad")
+    return dgate
+
+
+def sqmean_loss(x, want_grad=True):
+    lib = _lib.load()
+    _req(x, BF16, "x")
+    assert x.is_contiguous()
+    loss = torch.empty(1, device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x) if want_grad else None
+    ws = torch.empty(lib.otb_dot_blocks(), device=x.device, dtype=torch.float32)
+    check(lib.otb_sqmean_loss(_p(x), x.numel(), _p(loss), _p(dx), _p(ws), _stream()), "otb_sqmean_loss")
+    return loss, dx
+
+
+def im2col_patches(pixels, patch, Kpad):
+    assert pixels.is_cuda and pixels.dim() == 4 and pixels.shape[1] == 3
+    pixels = pixels.contiguous()
+    if pixels.dtype not in (torch.float32, BF16):
+        pixels = pixels.float()
+    N, _, H, W = pixels.shape
+    out = torch.empty((N * (H // patch) * (W // patch), Kpad), device=pixels.device, dtype=BF16)
+    check(_lib.load().otb_im2col_patches(_p(pixels), int(pixels.dtype == torch.float32), N, H, W, patch, _p(out), Kpad,
+                                         _stream()), "otb_im2col_patches")
+    return out
+
+
+def clip_assemble(patch_emb, cls, pos, N, np_):
+    D = patch_emb.shape[-1]
+    out = torch.empty((N, np_ + 1, D), device=patch_emb.device, dtype=BF16)
+    check(_lib.load().otb_clip_assemble(_p(_mat(patch_emb)), _p(_req(cls, torch.float32)), _p(_req(pos, torch.float32)),
+                                        _p(out), N, np_, D, _stream()), "otb_clip_assemble")
+    return out
+
+
+def media_from_clip(hidden, frame_embs, F):
+    """hidden bf16 [n_img, 1+v, D] -> bf16 [n_img*v, D] (CLS dropped, + frame_embs[img % F] if given)."""
+    _req(hidden, BF16, "hidden")
+    n_img, v1, D = hidden.shape
+    out = torch.empty((n_img * (v1 - 1), D), device=hidden.device, dtype=BF16)
+    check(_lib.load().otb_media_from_clip(_p(hidden.contiguous()), _p(frame_embs), F, _p(out), n_img, v1 - 1, D,
+                                          _stream()), "otb_media_from_clip")
+    return out
+
+
+def fuyu_scatter(word, cont, idx, b_off):
+    _req(word, BF16, "word"), _req(cont, BF16, "cont")
+    B, S, D = word.shape
+    out = torch.empty_like(word)
+    check(_lib.load().otb_fuyu_scatter(_p(word.contiguous()), _p(cont.contiguous()), _p(idx.contiguous()),
+                                       _p(b_off.contiguous()), _p(out), B, S, D, _stream()), "otb_fuyu_scatter")
+    return out
+
+
+def launch_count():
+    return int(_lib.load().otb_launch_count())
