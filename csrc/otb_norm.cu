@@ -229,6 +229,23 @@ __global__ void bcast_rows_kernel(const float* __restrict__ src, int div, int mo
     reinterpret_cast<uint4*>(out + static_cast<long long>(r) * D)[v] = pack8(f);
   }
 }
+
+// out[r,:] = x[r,:] + bias[(r/div)%mod,:]   (frame_embs broadcast add, modeling_otter.py:224-226)
+__global__ void add_rowbias_kernel(const bf16* __restrict__ x, const float* __restrict__ bias, int div, int mod,
+                                   bf16* __restrict__ out, int rows, int D) {
+  const int nvec = D >> 3;
+  const long long total = static_cast<long long>(rows) * nvec;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / nvec), v = static_cast<int>(i % nvec);
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * D) + v), f);
+    const float* s = bias + static_cast<long long>((r / div) % mod) * D + v * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s + 4));
+    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    reinterpret_cast<uint4*>(out + static_cast<long long>(r) * D)[v] = pack8(f);
+  }
+}
 // out[g, c] (+)= sum over rows r with (r/div)%mod == g.  block (32,8): 64 columns x 8 row lanes; grid (D/64, mod)
 __global__ void __launch_bounds__(256)
 grouped_colsum_kernel(const bf16* __restrict__ x, long long ldx, int rows, int D, int div, int mod,
@@ -507,6 +524,15 @@ extern "C" int otb_bcast_rows(const float* src, int div, int mod, void* out, int
   OTB_CHECK_ARG(src && out && div > 0 && mod > 0 && rows > 0 && D % 8 == 0, "otb_bcast_rows: bad argument");
   bcast_rows_kernel<<<grid_for(static_cast<long long>(rows) * (D / 8), 256), 256, 0, ST(stream)>>>(
       src, div, mod, static_cast<bf16*>(out), rows, D);
+  count_launch();
+  OTB_CHECK_CUDA(cudaGetLastError());
+  return OTB_OK;
+}
+extern "C" int otb_add_rowbias(const void* x, const float* bias, int div, int mod, void* out, int rows, int D,
+                               void* stream) {
+  OTB_CHECK_ARG(x && bias && out && div > 0 && mod > 0 && rows > 0 && D % 8 == 0, "otb_add_rowbias: bad argument");
+  add_rowbias_kernel<<<grid_for(static_cast<long long>(rows) * (D / 8), 256), 256, 0, ST(stream)>>>(
+      static_cast<const bf16*>(x), bias, div, mod, static_cast<bf16*>(out), rows, D);
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;

@@ -148,6 +148,8 @@ int otb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int otb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
 /* out[r,:] = bf16(src[(r / div) % mod, :])  fp32 [mod][D] -> bf16 [rows][D]; latents repeat (:232). */
 int otb_bcast_rows(const float* src, int div, int mod, void* out, int rows, int D, void* stream);
+/* out[r,:] = x[r,:] + bias[(r / div) % mod, :]   bf16 [rows][D] + fp32 [mod][D]  (frame_embs add, :224-226) */
+int otb_add_rowbias(const void* x, const float* bias, int div, int mod, void* out, int rows, int D, void* stream);
 /* out[g,:] (+)= sum_{r : (r/div)%mod == g} x[r,:]   bf16 [rows][D] -> fp32 [mod][D]
  * (gradient of latents repeat (:232) and of the frame_embs broadcast (:224-226)). Deterministic. */
 int otb_grouped_colsum(const void* x, int64_t ldx, int rows, int D, int div, int mod, float* out, int accumulate,

@@ -66,6 +66,7 @@ SIGNATURES = {
     "otb_cast_f32_bf16": (_I, [_VP, _VP, _I64, _VP]),
     "otb_cast_bf16_f32": (_I, [_VP, _VP, _I64, _VP]),
     "otb_bcast_rows": (_I, [_VP, _I, _I, _VP, _I, _I, _VP]),
+    "otb_add_rowbias": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP]),
     "otb_grouped_colsum": (_I, [_VP, _I64, _I, _I, _I, _I, _VP, _I, _VP]),
     "otb_dot_blocks": (_I, []),
     "otb_gate_grad": (_I, [_VP, _VP, _I64, _VP, _VP, _I, _VP, _VP]),

@@ -1,0 +1,68 @@
+"""Data parallelism of the hot path: one flat fp32 gradient buffer, ONE all-reduce per step.
+
+Replaces `accelerator.prepare(model)` + `accelerator.backward(loss)` (DDP bucketed all-reduce,
+pipeline/train/instruction_following.py:200,219-222,491-494): the batch dimension
+shards across ranks with no other collective.  Every trainable parameter's `.grad` is a view into one
+contiguous buffer; the wgrad GEMM epilogues write straight into it (`_otb_grad` sink, otter_b200.params),
+so the step ends with a single `all_reduce(AVG)` over NVLink/NVSwitch (NCCL via torch.distributed; on CPU
+tests the same code runs over gloo).
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradBuffer:
+    def __init__(self, params, device=None, dtype=torch.float32):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        device = device or self.params[0].device
+        # 16-byte aligned segments so vectorised epilogue stores stay legal
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.flat = torch.zeros(off, device=device, dtype=dtype)
+        for p, o in zip(self.params, self.offsets):
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            p.grad = view if p.dtype == dtype else None
+            if p.dtype in (torch.float32, torch.bfloat16) and dtype == torch.float32:
+                p._otb_grad = view          # sink used by otter_b200 backward kernels
+                p._otb_grad_live = False
+
+    def begin_step(self):
+        """Mark all sinks empty: the first writer overwrites, later writers accumulate (no zero-fill pass)."""
+        for p in self.params:
+            if hasattr(p, "_otb_grad"):
+                p._otb_grad_live = False
+
+    def finish_step(self):
+        """Sinks nobody wrote to (unused parameters) must read as zero before the reduce."""
+        for p in self.params:
+            if hasattr(p, "_otb_grad") and not p._otb_grad_live:
+                p._otb_grad.zero_()
+
+    def all_reduce(self, group=None, async_op=False):
+        """The one collective of the step: mean over ranks (DDP semantics)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        if dist.get_backend(group) == "gloo":          # gloo has no AVG
+            w = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            if not async_op:
+                self.flat.div_(dist.get_world_size(group))
+            return w
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+
+    def grad_norm(self):
+        return self.flat.norm()
+
+    def nbytes(self):
+        return self.flat.numel() * self.flat.element_size()
+
+
+def shard_batch(global_batch, rank, world_size):
+    """Contiguous, near-equal split of the batch dimension: rank r owns [start, stop)."""
+    base, rem = divmod(global_batch, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)

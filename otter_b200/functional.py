@@ -246,6 +246,16 @@ def bcast_rows(src, rows, div, mod):
     return out
 
 
+def add_rowbias(x, bias, div, mod):
+    x2 = _mat(x, "x")
+    assert x2.is_contiguous()
+    rows, D = x2.shape
+    out = torch.empty_like(x2)
+    check(_lib.load().otb_add_rowbias(_p(x2), _p(_req(bias, torch.float32, "bias")), div, mod, _p(out), rows, D,
+                                      _stream()), "otb_add_rowbias")
+    return out
+
+
 def grouped_colsum(x, div, mod, out=None, accumulate=False):
     x2 = _mat(x, "x")
     rows, D = x2.shape
