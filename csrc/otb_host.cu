@@ -76,4 +76,12 @@ const char* otb_last_error(void) { return otb::g_err; }
 int otb_version(void) { return 1; }
 int otb_compiled_arch(void) { return 100; }
 long long otb_launch_count(void) { return otb::g_launches.load(); }
+int otb_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(otb_gemm_epilogue);
+    case 1: return (int)sizeof(otb_attn_desc);
+    case 2: return (int)sizeof(otb_attn_grads);
+    default: return -1;
+  }
+}
 }

@@ -32,6 +32,9 @@ int otb_version(void);
 int otb_compiled_arch(void);
 /* Number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
 long long otb_launch_count(void);
+/* sizeof() of the ABI structs as the C compiler laid them out: 0 otb_gemm_epilogue, 1 otb_attn_desc,
+ * 2 otb_attn_grads (binding self-check for FFI hosts). */
+int otb_abi_sizeof(int which);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM:  D[M,N] = epilogue( A[M,K] . B[N,K]^T )      bf16 operands, fp32 accumulate in TMEM

@@ -55,6 +55,7 @@ SIGNATURES = {
     "otb_version": (_I, []),
     "otb_compiled_arch": (_I, []),
     "otb_launch_count": (C.c_longlong, []),
+    "otb_abi_sizeof": (_I, [_I]),
     "otb_gemm_bf16": (_I, [_VP, _I, _I64, _VP, _I, _I64, _I, _I, _I, C.POINTER(GemmEpilogue), _VP]),
     "otb_attn_fwd": (_I, [C.POINTER(AttnDesc), _VP]),
     "otb_attn_bwd": (_I, [C.POINTER(AttnDesc), C.POINTER(AttnGrads), _VP]),
@@ -93,6 +94,10 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
+    for i, st in enumerate((GemmEpilogue, AttnDesc, AttnGrads)):
+        if lib.otb_abi_sizeof(i) != C.sizeof(st):
+            raise OtbError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes in ctypes, "
+                           f"{lib.otb_abi_sizeof(i)} in the library")
     _lib = lib
     return lib
 

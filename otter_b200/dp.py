@@ -32,15 +32,20 @@ class FlatGradBuffer:
                 p._otb_grad_live = False
 
     def begin_step(self):
-        """Mark all sinks empty: the first writer overwrites, later writers accumulate (no zero-fill pass)."""
+        """Start a step.  Parameters whose gradients are written by otter_b200 kernels (`_otb_sink_user`, learned
+        on first use) are only marked empty — the first kernel write overwrites, later ones accumulate, so the
+        multi-GB buffer needs no zero-fill pass.  Parameters that receive gradients through plain autograd
+        accumulation (e.g. LM embeddings) are zeroed here, like optimizer.zero_grad()."""
         for p in self.params:
-            if hasattr(p, "_otb_grad"):
+            if getattr(p, "_otb_sink_user", False):
                 p._otb_grad_live = False
+            elif p.grad is not None:
+                p.grad.zero_()
 
     def finish_step(self):
-        """Sinks nobody wrote to (unused parameters) must read as zero before the reduce."""
+        """Kernel-written sinks nobody touched this step (unused parameters) must read as zero before the reduce."""
         for p in self.params:
-            if hasattr(p, "_otb_grad") and not p._otb_grad_live:
+            if getattr(p, "_otb_sink_user", False) and not p._otb_grad_live:
                 p._otb_grad.zero_()
 
     def all_reduce(self, group=None, async_op=False):

@@ -43,6 +43,15 @@ def _mat(t, name="matrix"):
 # ------------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------------
+_GEMM_PROF = None
+
+
+def set_gemm_profiler(sink):
+    """bench.py: when `sink` is a list, every GEMM launch appends (2*M*N*K, start_event, end_event)."""
+    global _GEMM_PROF
+    _GEMM_PROF = sink
+
+
 def _gemm_raw(A, a_mn, lda, B, b_mn, ldb, M, N, K, out, *, bias=None, act=0, aux_out=None, aux_in=None,
               scale_ptr=None, scale_tanh=False, alpha=1.0, residual=None, accumulate=False):
     lib = _lib.load()
@@ -62,8 +71,14 @@ def _gemm_raw(A, a_mn, lda, B, b_mn, ldb, M, N, K, out, *, bias=None, act=0, aux
     e.out_fp32 = 1 if out.dtype == torch.float32 else 0
     e.accumulate = 1 if accumulate else 0
     e.alpha = alpha
+    if _GEMM_PROF is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.otb_gemm_bf16(_p(A), int(a_mn), lda, _p(B), int(b_mn), ldb, M, N, K, C.byref(e), _stream()),
           "otb_gemm_bf16")
+    if _GEMM_PROF is not None:
+        e1.record()
+        _GEMM_PROF.append((2.0 * M * N * K, e0, e1))
     return out
 
 

@@ -10,12 +10,26 @@ carries `_otb_grad` (an fp32 view into the flat data-parallel gradient buffer, s
 the wgrad GEMM epilogue writes/accumulates straight into it and autograd receives None — no gather
 copy before the single NCCL all-reduce.
 """
+import weakref
+
 import torch
 
 from . import functional as F
 
-_shadow = {}   # id(param) -> (version, data_ptr, bf16 tensor)
+# id(param) -> (version, data_ptr, converted tensor, weakref(param)).  The weakref guards against CPython
+# re-using an id (and the allocator re-using the address) for a different parameter after the old one died.
+_shadow = {}
 _f32 = {}
+
+
+def _lookup(cache, p, ver, ptr):
+    hit = cache.get(id(p))
+    if hit is not None and hit[3]() is not p:
+        del cache[id(p)]
+        return None, None
+    if hit is not None and hit[0] == ver and hit[1] == ptr:
+        return hit, hit[2]
+    return hit, None
 
 
 def bf16_of(p):
@@ -23,14 +37,13 @@ def bf16_of(p):
     t = p.detach() if isinstance(p, torch.nn.Parameter) or p.requires_grad else p
     if t.dtype == torch.bfloat16:
         return t if t.is_contiguous() else t.contiguous()
-    key = id(p)
     ver, ptr = p._version, t.data_ptr()
-    hit = _shadow.get(key)
-    if hit is not None and hit[0] == ver and hit[1] == ptr:
-        return hit[2]
+    hit, val = _lookup(_shadow, p, ver, ptr)
+    if val is not None:
+        return val
     out = hit[2] if (hit is not None and hit[2].shape == t.shape and hit[2].device == t.device) else None
     out = F.cast_bf16(t.float() if t.dtype != torch.float32 else t, out)
-    _shadow[key] = (ver, ptr, out)
+    _shadow[id(p)] = (ver, ptr, out, weakref.ref(p))
     return out
 
 
@@ -39,14 +52,22 @@ def f32_of(p):
     t = p.detach()
     if t.dtype == torch.float32:
         return t if t.is_contiguous() else t.contiguous()
-    key = id(p)
     ver, ptr = p._version, t.data_ptr()
-    hit = _f32.get(key)
-    if hit is not None and hit[0] == ver and hit[1] == ptr:
-        return hit[2]
+    _, val = _lookup(_f32, p, ver, ptr)
+    if val is not None:
+        return val
     out = t.float().contiguous()
-    _f32[key] = (ver, ptr, out)
+    _f32[id(p)] = (ver, ptr, out, weakref.ref(p))
     return out
+
+
+def invalidate(params):
+    """Force the bf16 shadows of `params` to be re-derived on next use (what an optimizer step implies);
+    the shadow buffers themselves are kept and overwritten in place."""
+    for p in params:
+        hit = _shadow.get(id(p))
+        if hit is not None:
+            _shadow[id(p)] = (-1, hit[1], hit[2], hit[3])
 
 
 def clear_caches():
@@ -64,8 +85,9 @@ class GradSink:
         """-> (fp32 tensor to write, accumulate flag)."""
         buf = getattr(p, "_otb_grad", None)
         if buf is not None:
-            acc = bool(getattr(p, "_otb_grad_live", False))
+            acc = bool(getattr(p, "_otb_grad_live", False)) and bool(getattr(p, "_otb_sink_user", False))
             p._otb_grad_live = True
+            p._otb_sink_user = True
             return buf, acc
         if id(p) in self.returned:          # second contribution within the same backward
             return self.returned[id(p)], True

@@ -1,0 +1,67 @@
+"""CPU, world_size 2 over gloo: the N>1 path of otter_b200.dp — batch sharding and the single flat-buffer
+gradient all-reduce (mean over ranks = DDP semantics)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from otter_b200.dp import FlatGradBuffer, shard_batch
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                   # identical weights on all ranks
+    lin = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    lin[0].bias.requires_grad_(False)                      # a frozen parameter must be skipped
+    flat = FlatGradBuffer(lin.parameters(), device="cpu")
+    assert flat.numel % 4 == 0 and all(o % 4 == 0 for o in flat.offsets)
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(8, 6, generator=g)                     # the GLOBAL batch, same on both ranks
+    lo, hi = shard_batch(8, rank, world)
+    flat.begin_step()
+    loss = lin(X[lo:hi]).pow(2).mean()
+    loss.backward()                                        # autograd accumulates into the flat views
+    flat.finish_step()
+    flat.all_reduce()
+    # reference: full-batch gradient on one process (equal shards => mean of shard grads == full-batch grad)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    ref.load_state_dict(lin.state_dict())
+    ref(X).pow(2).mean().backward()
+    ok = all(torch.allclose(p.grad, r.grad, rtol=1e-5, atol=1e-6)
+             for p, r in zip(lin.parameters(), ref.parameters()) if p.requires_grad)
+    views_ok = all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in flat.params)
+    q.put((rank, ok, views_ok, flat.numel))
+    dist.destroy_process_group()
+
+
+def test_flat_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(ok and views for _, ok, views, _ in res), res
+    assert res[0][3] == res[1][3]
+
+
+def test_shard_batch_partitions_exactly():
+    for n in (1, 7, 8, 256):
+        for w in (1, 2, 3, 8):
+            spans = [shard_batch(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
