@@ -173,6 +173,12 @@ def run_cuda(args):
         flat.all_reduce()
         return loss
 
+    graphed = None
+    launches_per_step = None
+
+    def run_step():
+        return graphed.replay() if graphed is not None else step(d_vis, d_hid, d_loc)
+
     def timed(n, e2e):
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if world > 1:
@@ -180,13 +186,15 @@ def run_cuda(args):
         torch.cuda.synchronize()
         start.record()
         for _ in range(n):
-            if e2e:
-                v, h, l = h_vis.to(dev, non_blocking=True), h_hid.to(dev, non_blocking=True), h_loc.to(dev, non_blocking=True)
-                loss = step(v, h, l)
+            if e2e:                                      # pinned host -> static device inputs, step, loss -> host
+                d_vis.copy_(h_vis, non_blocking=True)
+                d_hid.copy_(h_hid, non_blocking=True)
+                d_loc.copy_(h_loc, non_blocking=True)
+                loss = run_step()
                 loss_host.copy_(loss, non_blocking=True)
                 torch.cuda.current_stream().synchronize()                   # the user reads the loss every step
             else:
-                step(d_vis, d_hid, d_loc)
+                run_step()
         end.record()
         if world > 1:
             dist.barrier()
@@ -198,16 +206,21 @@ def run_cuda(args):
             ms = t.item()
         return ms
 
+    n0 = F.launch_count()
+    step(d_vis, d_hid, d_loc)
+    launches_per_step = F.launch_count() - n0
+    if not args.no_graph:
+        from otter_b200.graph import GraphedStep
+        graphed = GraphedStep(step, d_vis, d_hid, d_loc)
     for _ in range(max(args.warmup, 3)):
-        step(d_vis, d_hid, d_loc)
+        run_step()
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    n0 = F.launch_count()
     ms = timed(args.steps, e2e=False)
-    launches = (F.launch_count() - n0) // args.steps
+    launches = launches_per_step
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(args.steps, e2e=True)
 
@@ -217,8 +230,19 @@ def run_cuda(args):
     step(d_vis, d_hid, d_loc)
     F.set_gemm_profiler(None)
     torch.cuda.synchronize()
-    g_flops = sum(f for f, _, _ in prof)
-    g_ms = sum(a.elapsed_time(b) for _, a, b in prof)
+    g_flops = sum(r[0] for r in prof)
+    g_ms = sum(r[1].elapsed_time(r[2]) for r in prof)
+    if rank == 0 and os.environ.get("OTB_GEMM_BREAKDOWN"):
+        agg = {}
+        for f, a, b, shape in prof:
+            t = agg.setdefault(shape, [0, 0.0, 0.0])
+            t[0] += 1
+            t[1] += a.elapsed_time(b)
+            t[2] += f
+        with open(os.environ["OTB_GEMM_BREAKDOWN"], "w") as fh:
+            fh.write("M,N,K,a_mn,b_mn,launches,total_ms,avg_us,TFLOPs\n")
+            for shape, (n, ms_, fl_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                fh.write(",".join(map(str, shape)) + f",{n},{ms_:.3f},{ms_ / n * 1e3:.1f},{fl_ / ms_ / 1e9:.1f}\n")
     if world > 1:
         dist.barrier()
 
@@ -246,6 +270,7 @@ def run_cuda(args):
                                "perceiver(6x64 latents) -> 8 gated x-attn blocks D=4096, fwd+bwd",
                    "per_gpu_batch": batch, "global_batch": batch * world, "L": CFG["L"], "images_per_sample": 1,
                    "parallelism": f"dp{world}", "random_init": True, "gates": 0.5,
+                   "launch": "eager" if args.no_graph else "whole step captured in one CUDA graph, replayed per step",
                    "weights": "fp32 master, bf16 compute copies re-cast every step; fp32 grads in one flat buffer",
                    "cache": "per-step working set (2.4 GB bf16 weights + activations) >> 126 MB L2; no explicit flush",
                    "grad_allreduce_bytes": flat.nbytes() if world > 1 else 0},
@@ -367,6 +392,7 @@ def main():
     ap.add_argument("--impl", default="otter_b200", choices=["otter_b200", "reference"])
     ap.add_argument("--per-gpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

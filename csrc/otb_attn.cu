@@ -71,6 +71,28 @@ __device__ __forceinline__ bool key_allowed(const AttnParams& p, int tt, int key
   return (key_idx / p.n_per_media + 1) == tt;
 }
 
+// Per-row key window inside one key tile, replacing a per-element mask test (and its integer division):
+//   class 0 -> empty; class 2 (uniform) -> every valid key with weight 1; class 1 -> exp() over [lo, hi)
+struct RowRange {
+  int lo, hi;
+};
+__device__ __forceinline__ RowRange row_range(const AttnParams& p, int cls, int tt, const KeyTile& kt) {
+  RowRange r;
+  r.lo = 0;
+  r.hi = (cls == 0) ? 0 : kt.valid;
+  if (cls == 1 && p.text_time != nullptr) {
+    const int s0 = (tt - 1) * p.n_per_media - kt.key_base;
+    r.lo = max(0, s0);
+    r.hi = max(r.lo, min(kt.valid, s0 + p.n_per_media));
+  }
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // write 8 consecutive bf16 (one 16 B unit) of row r, columns [c, c+8) into a [rows][64] SW128 tile chunk
 __device__ __forceinline__ void st_sw128(uint8_t* chunk_base, int r, int c_in_chunk, uint4 v) {
   const int unit = (c_in_chunk >> 3) ^ (r & 7);
@@ -168,6 +190,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const bool is_p2 = (nt == 1) || (s >= nt);
     const bool do_max = (nt == 1) || (s < nt);
     const KeyTile kt = key_tile(p, prob, j, nt1);
+    const RowRange rr = row_range(p, cls, tt, kt);
     if (do_max) {
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -178,12 +201,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int cc = c * 32 + i;
-            if (cc < kt.valid && key_allowed(p, tt, kt.key_base + cc)) m_run = fmaxf(m_run, __uint_as_float(r[i]));
+            if (cc >= rr.lo && cc < rr.hi) m_run = fmaxf(m_run, __uint_as_float(r[i]));
           }
         }
       }
     }
     if (is_p2) {
+      const float mb2 = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;   // m_run is final here
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
@@ -194,13 +218,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int i = 0; i < 32; ++i) {
           const int cc = c * 32 + i;
           float v = 0.f;
-          if (cc < kt.valid) {
-            if (cls == 1) {
-              if (key_allowed(p, tt, kt.key_base + cc)) v = exp2f((__uint_as_float(r[i]) - m_run) * p.scale_log2);
-            } else if (cls == 2) {
-              v = 1.0f;
-            }
-          }
+          if (cc >= rr.lo && cc < rr.hi)
+            v = (cls == 1) ? ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb2)) : 1.0f;
           pv[i] = v;
           l_run += v;
         }
@@ -260,6 +279,221 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
+  }
+}
+
+// ================================================================================================
+// forward, S-resident variant (<= 3 key tiles = 384 keys: CLIP S=257, perceiver image 320, gated x-attn)
+//   All K/V tiles are TMA-loaded up front; every S_j = Q K_j^T stays in TMEM (128 columns per tile), so the
+//   softmax needs no second QK^T pass and no O rescaling.  256 threads: warps w and w+4 share TMEM lane
+//   quarter w%4 and split the 128 key columns of a tile in halves; row max / row sum are combined through smem.
+//   P tiles are double-buffered so softmax(tile j+1) overlaps the P V MMA of tile j.
+// ================================================================================================
+constexpr int kResThreads = 256;
+__global__ void __launch_bounds__(kResThreads)
+attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv1,
+                         const __grid_constant__ CUtensorMap map_kv2, AttnParams p, int nt, int tmem_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;                              // 16 KB
+  uint8_t* s_k = s_q + kTileBytes;                  // nt x 16 KB
+  uint8_t* s_v = s_k + nt * kTileBytes;             // nt x 16 KB
+  uint8_t* s_p = s_v + nt * kTileBytes;             // 2 x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 4 * kTileBytes);
+  uint64_t* full_k = bars;          // [3]
+  uint64_t* full_v = bars + 3;      // [3]
+  uint64_t* bar_q = bars + 6;
+  uint64_t* bar_s = bars + 7;       // [3]
+  uint64_t* bar_pv = bars + 10;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  __shared__ float red[256];                          // [2][128] row partials
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, prob = blockIdx.z;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int r_in_tile = quarter * 32 + lane;
+
+  if (tid == 32) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&full_k[i], 1); mbar_init(&full_v[i], 1); mbar_init(&bar_s[i], 1); }
+    mbar_init(bar_q, 1); mbar_init(&bar_pv[0], 1); mbar_init(&bar_pv[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_o = tmem + nt * 128;
+  const int nt1 = (p.Sk1 + 127) / 128;
+
+  const int row = qt * 128 + r_in_tile;
+  const bool row_ok = row < p.Sq;
+  int tt = 0;
+  if (p.text_time != nullptr && row_ok) tt = p.text_time[prob * p.Sq + row];
+  const int cls = row_ok ? row_class(p, tt) : 0;
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_kv1); tma_prefetch_desc(&map_kv2);
+    mbar_arrive_expect_tx(bar_q, kTileBytes);
+    tma_load_2d(s_q, &map_q, bar_q, p.q_col0 + h * 64, prob * p.Sq + qt * 128);
+    for (int j = 0; j < nt; ++j) {
+      const KeyTile kt = key_tile(p, prob, j, nt1);
+      const CUtensorMap* m = kt.src ? &map_kv2 : &map_kv1;
+      mbar_arrive_expect_tx(&full_k[j], kTileBytes);
+      tma_load_2d(s_k + j * kTileBytes, m, &full_k[j], (kt.src ? p.k2_col0 : p.k1_col0) + h * 64, kt.row0);
+    }
+    for (int j = 0; j < nt; ++j) {
+      const KeyTile kt = key_tile(p, prob, j, nt1);
+      const CUtensorMap* m = kt.src ? &map_kv2 : &map_kv1;
+      mbar_arrive_expect_tx(&full_v[j], kTileBytes);
+      tma_load_2d(s_v + j * kTileBytes, m, &full_v[j], (kt.src ? p.v2_col0 : p.v1_col0) + h * 64, kt.row0);
+    }
+    mbar_wait(bar_q, 0);
+    const uint64_t da = make_smem_desc(smem_u32(s_q), 16, 1024);
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&full_k[j], 0);
+      tc_fence_after();
+      const uint64_t db = make_smem_desc(smem_u32(s_k + j * kTileBytes), 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem + j * 128, da + k * 2, db + k * 2, idesc_s, k != 0);
+      umma_commit(&bar_s[j]);
+    }
+  }
+
+  const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+  // ---- sweep 1: row max over all resident tiles (this thread: 64 of the 128 columns of each tile) ----
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  for (int j = 0; j < nt; ++j) {
+    mbar_wait(&bar_s[j], 0);
+    tc_fence_after();
+    const KeyTile kt = key_tile(p, prob, j, nt1);
+    const RowRange rr = row_range(p, cls, tt, kt);
+    const bool whole = __all_sync(0xffffffffu, cls == 1 && rr.lo == 0 && rr.hi == 128);
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem + lane_addr + j * 128 + half * 64 + c * 32, r);
+      tmem_ld_wait();
+      if (whole) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx[0] = fmaxf(mx[0], __uint_as_float(r[i]));     mx[1] = fmaxf(mx[1], __uint_as_float(r[i + 1]));
+          mx[2] = fmaxf(mx[2], __uint_as_float(r[i + 2])); mx[3] = fmaxf(mx[3], __uint_as_float(r[i + 3]));
+        }
+      } else if (cls == 1) {
+        const int c0 = half * 64 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int cc = c0 + i;
+          if (cc >= rr.lo && cc < rr.hi) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+        }
+      }
+    }
+  }
+  float m_run = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+  red[half * 128 + r_in_tile] = m_run;
+  __syncthreads();
+  m_run = fmaxf(red[r_in_tile], red[128 + r_in_tile]);
+  __syncthreads();
+
+  // ---- sweep 2: P = exp2((S - m) * scale*log2e), O += P V ----
+  float ls[4] = {0.f, 0.f, 0.f, 0.f};
+  const float mb = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
+  for (int j = 0; j < nt; ++j) {
+    const KeyTile kt = key_tile(p, prob, j, nt1);
+    const RowRange rr = row_range(p, cls, tt, kt);
+    const bool whole = __all_sync(0xffffffffu, cls == 1 && rr.lo == 0 && rr.hi == 128);
+    uint8_t* pbuf = s_p + (j & 1) * 2 * kTileBytes;
+    if (j >= 2) mbar_wait(&bar_pv[j & 1], 0);          // P buffer (j-2) consumed
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem + lane_addr + j * 128 + half * 64 + c * 32, r);
+      tmem_ld_wait();
+      float pv[32];
+      if (whole) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+          ls[i & 3] += pv[i];
+        }
+      } else {
+        const int c0 = half * 64 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int cc = c0 + i;
+          float v = 0.f;
+          if (cc >= rr.lo && cc < rr.hi) v = (cls == 1) ? ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb)) : 1.0f;
+          pv[i] = v;
+          ls[i & 3] += v;
+        }
+      }
+      uint8_t* chunk = pbuf + half * kTileBytes;       // 64-key chunk == this thread's column half
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]); o.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
+        o.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]); o.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
+        st_sw128(chunk, r_in_tile, c * 32 + g * 8, o);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(&full_v[j], 0);
+      tc_fence_after();
+      const uint64_t db = make_smem_desc(smem_u32(s_v + j * kTileBytes), 16, 1024);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint64_t da = make_smem_desc(smem_u32(pbuf + (k >> 2) * kTileBytes) + (k & 3) * 32, 16, 1024);
+        umma_bf16(t_o, da, db + k * 128, idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
+      }
+      umma_commit(&bar_pv[j & 1]);
+    }
+  }
+  float l_run = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+  red[half * 128 + r_in_tile] = l_run;
+  // last P V must have retired before O is read: tile nt-1 is the (count)th completion of its barrier
+  {
+    const int jl = nt - 1;
+    mbar_wait(&bar_pv[jl & 1], (jl >> 1) & 1);
+    if (nt >= 2) { const int j2 = nt - 2; mbar_wait(&bar_pv[j2 & 1], (j2 >> 1) & 1); }
+  }
+  tc_fence_after();
+  __syncthreads();
+  l_run = red[r_in_tile] + red[128 + r_in_tile];
+  const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+  {
+    uint32_t r[32];
+    tmem_ld32(t_o + lane_addr + half * 32, r);
+    tmem_ld_wait();
+    if (row_ok) {
+      bf16* dst = p.out + static_cast<long long>(prob * p.Sq + row) * p.ldo + p.o_col0 + h * 64 + half * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
+        o.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
+        o.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
+        o.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(dst + g * 8) = o;
+      }
+    }
+  }
+  if (half == 0 && row_ok && p.lse != nullptr) {
+    p.lse[(static_cast<long long>(prob) * p.H + h) * p.Sq + row] =
+        (cls == 1 && l_run > 0.f) ? (m_run * p.scale + logf(l_run)) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, tmem_cols);
   }
 }
 
@@ -347,6 +581,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       const int cls = row_ok ? row_class(p, tt) : 0;
       const float inv_cnt = 1.0f / static_cast<float>(p.Sk1 + p.Sk2);
+      const RowRange rr = row_range(p, cls, tt, kt);
+      const float lse_l2 = lse * 1.4426950408889634f;
 
       if (tid == 0) {
         if (i == 0) { mbar_wait(bar_kv, ph_kv); }
@@ -382,13 +618,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int e = 0; e < 8; ++e) {
             const int cc = c * 32 + g * 8 + e;
             float pr = 0.f, ds = 0.f;
-            if (cc < kt.valid) {
+            if (cc >= rr.lo && cc < rr.hi) {
               if (cls == 1) {
-                if (key_allowed(p, tt, kt.key_base + cc)) {
-                  pr = __expf(__uint_as_float(rs[g * 8 + e]) * p.scale - lse);
-                  ds = pr * (__uint_as_float(rp[g * 8 + e]) - delta) * p.scale;
-                }
-              } else if (cls == 2) {
+                pr = ex2_approx(fmaf(__uint_as_float(rs[g * 8 + e]), p.scale_log2, -lse_l2));
+                ds = pr * (__uint_as_float(rp[g * 8 + e]) - delta) * p.scale;
+              } else {
                 pr = inv_cnt;
               }
             }
@@ -556,10 +790,20 @@ extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
   static bool attr = false;
   if (!attr) {
     OTB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwdSmem));
+    OTB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (1 + 2 * 3 + 4) * kTileBytes + 1024 + 2048));
     attr = true;
   }
   dim3 grid((d->Sq + 127) / 128, d->H, d->P);
-  attn_fwd_kernel<<<grid, kAttnThreads, kAttnFwdSmem, static_cast<cudaStream_t>(stream)>>>(mq, mk1, mk2, p);
+  const int nt = (d->Sk1 + 127) / 128 + (d->Sk2 + 127) / 128;
+  if (nt <= 3) {
+    const int smem = (1 + 2 * nt + 4) * kTileBytes + 1024 + 2048;
+    const int tmem_cols = (nt == 1) ? 256 : 512;
+    attn_fwd_resident_kernel<<<grid, kResThreads, smem, static_cast<cudaStream_t>(stream)>>>(mq, mk1, mk2, p, nt,
+                                                                                             tmem_cols);
+  } else {
+    attn_fwd_kernel<<<grid, kAttnThreads, kAttnFwdSmem, static_cast<cudaStream_t>(stream)>>>(mq, mk1, mk2, p);
+  }
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;

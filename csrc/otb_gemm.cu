@@ -8,11 +8,14 @@
 //   wgrad    dW = dy^T x     : A = dy read MN-major,    B = x  read MN-major (reduction over tokens)
 // (reference: modeling_otter.py:139-148,164-184,253-256,284-288,340,363-370; clip.py:106-149)
 //
-// Structure (one CTA per SM, persistent over output tiles, 256 threads):
-//   warp 0   : TMA producer   — cp.async.bulk.tensor 128B-swizzled tiles into a kStages-deep smem ring
-//   warp 1   : MMA issuer     — one thread issues tcgen05.mma (128 x BN x 16), tcgen05.commit frees smem slots
-//   warp 2   : TMEM allocator — 2 x BN fp32 columns (double-buffered accumulator)
-//   warps 4-7: epilogue       — tcgen05.ld 32 lanes x 32 columns, fused bias/GELU/gate/residual, 16 B stores
+// Structure (one CTA per SM, persistent over output tiles, 384 threads):
+//   warp 10  : TMA producer   — cp.async.bulk.tensor 128B-swizzled tiles into a kStages-deep smem ring
+//   warp 11  : MMA issuer     — one thread issues tcgen05.mma (128 x BN x 16), tcgen05.commit frees smem slots
+//                               (highest warp ids: the issue arbiter favours them over the math-heavy epilogue)
+//   warp 8   : TMEM allocator — 2 x BN fp32 columns (double-buffered accumulator)
+//   warps 0-7: epilogue       — tcgen05.ld 32 lanes x 32 columns (two warps per TMEM lane quarter, each half of
+//                               the tile's columns), global operands prefetched per chunk, fused
+//                               bias/GELU/gate/residual, 16 B stores
 // The accumulator double buffer lets the epilogue of tile i overlap the main loop of tile i+1.
 #include "otb_common.cuh"
 #include "otb_host.h"
@@ -21,7 +24,7 @@ namespace otb {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;   // 8 epilogue warps + 4 control warps
 
 struct GemmEpi {
   const float* bias;
@@ -76,17 +79,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 8) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 10 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -116,7 +119,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 11 && lane == 0) {
     // ===================== MMA issuer (single thread) =====================
     constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, A_MN, B_MN);
     constexpr uint32_t a_lbo = A_MN ? kBK * 128 : 16, a_sbo = 1024, a_kstep = A_MN ? 2048 : 32;
@@ -146,9 +149,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+  } else if (warp < 8) {
+    // ===================== epilogue warps (8): warp w -> TMEM lane quarter w%4, column half w/4 =========
+    const int q = warp & 3;
+    const int half = warp >> 2;
     float scale = ep.alpha;
     if (ep.scale_ptr != nullptr) {
       const float s = __ldg(ep.scale_ptr);
@@ -165,13 +169,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const long long lrow = row;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+        const int colbase = n0 + c * 32;
+        const bool act_chunk = row_ok && colbase < N;
+        // Issue every global read of this 32-column chunk up front (they do not depend on the accumulator):
+        // each thread reads 64 B of its own row, so the loads of a warp are uncoalesced — what matters is
+        // having all of them in flight together instead of one dependent load per 8 columns.
+        uint4 res[4], aux[4];
+        float4 old[8];
+        if (act_chunk) {
+          if (ep.residual != nullptr) {
+            const uint4* pr = reinterpret_cast<const uint4*>(ep.residual + lrow * ep.ld_res + colbase);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) res[g] = __ldg(pr + g);
+          }
+          if (ep.aux_in != nullptr) {
+            const uint4* pa = reinterpret_cast<const uint4*>(ep.aux_in + lrow * ep.ld_aux_in + colbase);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) aux[g] = __ldg(pa + g);
+          }
+          if (ep.out_fp32 && ep.accumulate) {
+            const float4* po = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ep.out) + lrow * ep.ld_out + colbase);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) if (colbase + g * 4 < N) old[g] = po[g];
+          }
+        }
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        const int colbase = n0 + c * 32;
-        if (row_ok && colbase < N) {
+        if (act_chunk) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = colbase + g * 8;
@@ -189,7 +217,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               uint4 o;
               o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
               o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(ep.aux_out + static_cast<long long>(row) * ep.ld_aux_out + col) = o;
+              *reinterpret_cast<uint4*>(ep.aux_out + lrow * ep.ld_aux_out + col) = o;
             }
             if (ep.act == 1) {
 #pragma unroll
@@ -199,10 +227,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
             }
             if (ep.aux_in != nullptr) {
-              const uint4 a = __ldg(
-                  reinterpret_cast<const uint4*>(ep.aux_in + static_cast<long long>(row) * ep.ld_aux_in + col));
-              const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
-                           a3 = unpack_bf16x2(a.w);
+              const float2 a0 = unpack_bf16x2(aux[g].x), a1 = unpack_bf16x2(aux[g].y), a2 = unpack_bf16x2(aux[g].z),
+                           a3 = unpack_bf16x2(aux[g].w);
               v[0] *= gelu_erf_grad(a0.x); v[1] *= gelu_erf_grad(a0.y);
               v[2] *= gelu_erf_grad(a1.x); v[3] *= gelu_erf_grad(a1.y);
               v[4] *= gelu_erf_grad(a2.x); v[5] *= gelu_erf_grad(a2.y);
@@ -211,23 +237,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= scale;
             if (ep.residual != nullptr) {
-              const uint4 a = __ldg(
-                  reinterpret_cast<const uint4*>(ep.residual + static_cast<long long>(row) * ep.ld_res + col));
-              const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
-                           a3 = unpack_bf16x2(a.w);
+              const float2 a0 = unpack_bf16x2(res[g].x), a1 = unpack_bf16x2(res[g].y), a2 = unpack_bf16x2(res[g].z),
+                           a3 = unpack_bf16x2(res[g].w);
               v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
               v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
             }
             if (ep.out_fp32) {
-              float* o = reinterpret_cast<float*>(ep.out) + static_cast<long long>(row) * ep.ld_out + col;
-              float4 o0, o1;
-              if (ep.accumulate) {
-                o0 = *reinterpret_cast<const float4*>(o);
-                o1 = *reinterpret_cast<const float4*>(o + 4);
-              } else {
-                o0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                o1 = o0;
-              }
+              float* o = reinterpret_cast<float*>(ep.out) + lrow * ep.ld_out + col;
+              float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+              if (ep.accumulate) { o0 = old[2 * g]; o1 = old[2 * g + 1]; }
               o0.x += v[0]; o0.y += v[1]; o0.z += v[2]; o0.w += v[3];
               o1.x += v[4]; o1.y += v[5]; o1.z += v[6]; o1.w += v[7];
               *reinterpret_cast<float4*>(o) = o0;
@@ -236,8 +254,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               uint4 o;
               o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
               o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + static_cast<long long>(row) * ep.ld_out +
-                                        col) = o;
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + lrow * ep.ld_out + col) = o;
             }
           }
         }
@@ -250,7 +267,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }

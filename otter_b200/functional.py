@@ -78,7 +78,7 @@ def _gemm_raw(A, a_mn, lda, B, b_mn, ldb, M, N, K, out, *, bias=None, act=0, aux
           "otb_gemm_bf16")
     if _GEMM_PROF is not None:
         e1.record()
-        _GEMM_PROF.append((2.0 * M * N * K, e0, e1))
+        _GEMM_PROF.append((2.0 * M * N * K, e0, e1, (M, N, K, int(a_mn), int(b_mn))))
     return out
 
 
