@@ -130,6 +130,46 @@ def host_batch(batch, rank):
     return vision_x.pin_memory(), hidden.pin_memory(), loc.pin_memory()
 
 
+def dominant_gemm_times(dev, M, D):
+    from otter_b200 import functional as F
+    g = torch.Generator(device=dev).manual_seed(1)
+
+    def rn(*shape, scale=1.0):
+        return (torch.randn(*shape, device=dev, generator=g) * scale).to(torch.bfloat16)
+
+    x, h, dy, dz = rn(M, D), rn(M, 4 * D), rn(M, D), rn(M, 4 * D)
+    w1, w2 = rn(4 * D, D, scale=D ** -0.5), rn(D, 4 * D, scale=(4 * D) ** -0.5)
+    z, a2 = torch.empty(M, 4 * D, device=dev, dtype=torch.bfloat16), torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    gw1 = torch.zeros(4 * D, D, device=dev)
+    gw2 = torch.zeros(D, 4 * D, device=dev)
+    gate = torch.full((1,), 0.5, device=dev)
+    calls = {
+        "fwd_up_gelu": lambda: F.linear_fwd(x, w1, act=1, aux_out=z),
+        "fwd_down_gate_res": lambda: F.linear_fwd(h, w2, aux_out=a2, scale_ptr=gate, scale_tanh=True, residual=x),
+        "dgrad_down_dgelu": lambda: F.linear_dgrad(dy, w2, aux_in=z, scale_ptr=gate, scale_tanh=True),
+        "dgrad_up": lambda: F.linear_dgrad(dz, w1),
+        "wgrad_down": lambda: F.linear_wgrad(dy, h, out=gw2, accumulate=False, scale_ptr=gate, scale_tanh=True),
+        "wgrad_up": lambda: F.linear_wgrad(dz, x, out=gw1, accumulate=False),
+    }
+    F.linear_fwd(x, w1, act=1, aux_out=z)        # realistic pre-activations for the dGELU epilogue
+    per, tot_ms = {}, 0.0
+    flops = 2.0 * M * D * 4 * D
+    for name, fn in calls.items():
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        per[name] = round(ms * 1e3, 1)
+        tot_ms += ms
+    return {"tflops": 6 * flops / (tot_ms * 1e-3) / 1e12, "per_class_us": per, "sum_ms": tot_ms, "flops_avg": flops}
+
+
 def run_cuda(args):
     import torch.distributed as dist
     from otter_b200 import functional as F
@@ -170,14 +210,19 @@ def run_cuda(args):
         loss, dx = F.sqmean_loss(x)
         x.backward(dx)
         flat.finish_step()
-        flat.all_reduce()
         return loss
+
+    def log(msg):
+        if rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
 
     graphed = None
     launches_per_step = None
 
     def run_step():
-        return graphed.replay() if graphed is not None else step(d_vis, d_hid, d_loc)
+        loss = graphed.replay() if graphed is not None else step(d_vis, d_hid, d_loc)
+        flat.all_reduce()          # the one collective of the step (NCCL, outside the captured graph)
+        return loss
 
     def timed(n, e2e):
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -206,12 +251,15 @@ def run_cuda(args):
             ms = t.item()
         return ms
 
+    log(f"modules built (world {world}, per-GPU batch {batch})")
+    step(d_vis, d_hid, d_loc)                 # first step also builds the frozen CLIP weight shadows
     n0 = F.launch_count()
     step(d_vis, d_hid, d_loc)
     launches_per_step = F.launch_count() - n0
     if not args.no_graph:
         from otter_b200.graph import GraphedStep
         graphed = GraphedStep(step, d_vis, d_hid, d_loc)
+        log("step captured as CUDA graph")
     for _ in range(max(args.warmup, 3)):
         run_step()
     torch.cuda.synchronize()
@@ -220,24 +268,30 @@ def run_cuda(args):
     if sampler:
         sampler.start()
     ms = timed(args.steps, e2e=False)
+    log(f"timed region done: {ms / args.steps:.3f} ms/step")
     launches = launches_per_step
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(args.steps, e2e=True)
 
-    # ---- roofline of the dominant kernel (GEMM): live CUDA events around every GEMM launch of one step ----
+    # ---- roofline of the dominant kernel: the six 4096<->16384 FFN GEMM launch classes of the gated blocks
+    # (8 launches each per step, 86 % of the step's algorithmic FLOPs), each timed live with CUDA events over
+    # 10 back-to-back launches on fresh N(0,1) operands (operands + outputs > L2) ----
+    dom = dominant_gemm_times(dev, B * L, D) if rank == 0 else None
+    # eager per-launch event timing of EVERY GEMM of one step (includes host launch gaps; kept as a cross-check)
     prof = []
     F.set_gemm_profiler(prof)
     step(d_vis, d_hid, d_loc)
+    flat.all_reduce()
     F.set_gemm_profiler(None)
     torch.cuda.synchronize()
     g_flops = sum(r[0] for r in prof)
     g_ms = sum(r[1].elapsed_time(r[2]) for r in prof)
     if rank == 0 and os.environ.get("OTB_GEMM_BREAKDOWN"):
         agg = {}
-        for f, a, b, shape in prof:
+        for f, a_, b_, shape in prof:
             t = agg.setdefault(shape, [0, 0.0, 0.0])
             t[0] += 1
-            t[1] += a.elapsed_time(b)
+            t[1] += a_.elapsed_time(b_)
             t[2] += f
         with open(os.environ["OTB_GEMM_BREAKDOWN"], "w") as fh:
             fh.write("M,N,K,a_mn,b_mn,launches,total_ms,avg_us,TFLOPs\n")
@@ -255,13 +309,15 @@ def run_cuda(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)     # kernel timed inside a long step -> sustained figure
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md sustained)"
+    peak_tf = peaks.get("bf16_tflops", 1590.0)                # kernel timed alone -> burst figure
+    peak_sus = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else \
+        "fallback 1590 TFLOP/s (B200_PROFILING.md)"
     step_ms = ms / args.steps
     value = batch * world * args.steps / (ms / 1e3)
     e2e_value = batch * world * args.steps / (ms_e2e / 1e3)
     fl = flops_per_sample(CFG["L"], CFG["D"], CFG["T"], CFG["F"], CFG["n_gated"])
-    ach = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    ach = dom["tflops"]
     out = {
         "metric": "samples/sec perceiver+gated-xattn fwd+bwd", "value": round(value, 2), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(step_ms, 3),
@@ -270,7 +326,8 @@ def run_cuda(args):
                                "perceiver(6x64 latents) -> 8 gated x-attn blocks D=4096, fwd+bwd",
                    "per_gpu_batch": batch, "global_batch": batch * world, "L": CFG["L"], "images_per_sample": 1,
                    "parallelism": f"dp{world}", "random_init": True, "gates": 0.5,
-                   "launch": "eager" if args.no_graph else "whole step captured in one CUDA graph, replayed per step",
+                   "launch": "eager" if args.no_graph else "fwd+bwd of the step captured in one CUDA graph, replayed per step"
+                             + ("; NCCL all-reduce issued after the replay" if world > 1 else ""),
                    "weights": "fp32 master, bf16 compute copies re-cast every step; fp32 grads in one flat buffer",
                    "cache": "per-step working set (2.4 GB bf16 weights + activations) >> 126 MB L2; no explicit flush",
                    "grad_allreduce_bytes": flat.nbytes() if world > 1 else 0},
@@ -279,12 +336,19 @@ def run_cuda(args):
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "otb::gemm_bf16_kernel (tcgen05/TMA GEMM, all launches of a step)",
+        "roofline": {"bound": "tensor",
+                     "kernel": "otb::gemm_bf16_kernel<256,*,*> — the six 4096<->16384 FFN GEMM classes (fwd, dgrad, "
+                               "wgrad) of the gated blocks, 48 launches/step",
                      "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": round(ach / peak_tf, 4) if peak_tf else None, "traffic": None,
-                     "peak_source": peak_src, "gemm_launches": len(prof), "gemm_ms_per_step": round(g_ms, 3),
-                     "gemm_share_of_step": round(g_ms / step_ms, 3),
-                     "step_algorithmic_tflops": round(fl * batch / (step_ms * 1e-3) / 1e12, 1)},
+                     "frac": round(ach / peak_tf, 4) if peak_tf else None,
+                     "traffic": 252.5e6, "traffic_note": "dram read+write of one 2048x16384x4096 launch, ncu --set full, "
+                                                         "profiles/r01_ncu_gemm_full.md (algorithmic 285 MB)",
+                     "peak_source": peak_src, "frac_of_sustained_peak": round(ach / peak_sus, 4),
+                     "per_class_us": dom["per_class_us"], "flops_per_launch_avg": dom["flops_avg"],
+                     "share_of_step": round(8 * dom["sum_ms"] / step_ms, 3),
+                     "all_gemms_eager_event_ms": round(g_ms, 3), "all_gemm_launches": len(prof),
+                     "step_algorithmic_tflops": round(fl * batch / (step_ms * 1e-3) / 1e12, 1),
+                     "step_frac_of_sustained_peak": round(fl * batch / (step_ms * 1e-3) / 1e12 / peak_sus, 4)},
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_port_sample(steps=1, warmup=0, batch=1)

@@ -17,6 +17,8 @@
 //                               the tile's columns), global operands prefetched per chunk, fused
 //                               bias/GELU/gate/residual, 16 B stores
 // The accumulator double buffer lets the epilogue of tile i overlap the main loop of tile i+1.
+#include <cstdlib>
+
 #include "otb_common.cuh"
 #include "otb_host.h"
 
@@ -48,7 +50,10 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// MC = true: clusters of 2 CTAs work on two vertically adjacent 128-row tiles of the same BN-wide column block;
+// each CTA fetches half of the shared B tile and TMA-multicasts it to both, which cuts the L2->SM operand
+// traffic per FLOP by a third (the big GEMMs are L2-bandwidth bound at one 128xBN tile per CTA).
+template <int BN, bool A_MN, bool B_MN, bool MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
                  int K, GemmEpi ep) {
@@ -65,17 +70,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = (M + kBM - 1) / kBM;
+  const int tiles_m_real = (M + kBM - 1) / kBM;
+  const int tiles_m = MC ? ((tiles_m_real + 1) & ~1) : tiles_m_real;   // MC: pad to whole CTA pairs (OOB rows = 0)
   const int tiles_n = (N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + kBK - 1) / kBK;
+  const uint32_t cta_rank = MC ? cluster_ctarank() : 0;
+  // persistent schedule: consecutive tile ids run down M, so with MC the pair (2i, 2i+1) shares its column block;
+  // blockIdx.x of a cluster is (2c, 2c+1) and gridDim.x is even -> both CTAs walk the same number of tiles.
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC ? 2 : 1);   // MC: both CTAs of the pair must have consumed the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -86,6 +95,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 8) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();       // peer barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -109,12 +119,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int c = 0; c < kBM / 64; ++c)                  // box {64 m, 64 k rows} per 64-wide chunk
             tma_load_2d(sa + c * (kBK * 128), &map_a, &full_bar[stage], m0 + c * 64, k0);
         }
-        if constexpr (!B_MN) {
-          tma_load_2d(sb, &map_b, &full_bar[stage], k0, n0);  // box {64 k, BN rows}
-        } else {
+        if constexpr (!MC) {
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &map_b, &full_bar[stage], k0, n0);  // box {64 k, BN rows}
+          } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c)
-            tma_load_2d(sb + c * (kBK * 128), &map_b, &full_bar[stage], n0 + c * 64, k0);
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * (kBK * 128), &map_b, &full_bar[stage], n0 + c * 64, k0);
+          }
+        } else {  // this CTA's half of the B tile, multicast into both CTAs of the pair
+          if constexpr (!B_MN) {
+            tma_load_2d_mcast(sb + cta_rank * (BN / 2) * 128, &map_b, &full_bar[stage], k0,
+                              n0 + cta_rank * (BN / 2), 0x3);  // box {64 k, BN/2 rows}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 128; ++c) {
+              const int cc = cta_rank * (BN / 128) + c;
+              tma_load_2d_mcast(sb + cc * (kBK * 128), &map_b, &full_bar[stage], n0 + cc * 64, k0, 0x3);
+            }
+          }
         }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
@@ -144,7 +167,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int k = 0; k < kBK / 16; ++k) {
           umma_bf16(d_tmem, da + ((k * a_kstep) >> 4), db + ((k * b_kstep) >> 4), idesc, (kb | k) != 0);
         }
-        umma_commit(&empty_bar[stage]);  // frees this smem slot once the MMAs above retire
+        if constexpr (MC) umma_commit_mcast(&empty_bar[stage], 0x3);   // release the slot in BOTH CTAs
+        else umma_commit(&empty_bar[stage]);  // frees this smem slot once the MMAs above retire
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
       umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
@@ -267,13 +291,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();       // no CTA leaves while its peer may still signal / write into it
   if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool MC>
 static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                        const GemmEpi& ep, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -282,20 +307,34 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   if (!A_MN) rc = make_tmap_bf16_2d(&ma, A, M, K, lda, kBM, 64);   // [M][K], box 128 rows x 64 k
   else       rc = make_tmap_bf16_2d(&ma, A, K, M, lda, kBK, 64);   // [K][M], box 64 k-rows x 64 m
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap_bf16_2d(&mb, B, N, K, ldb, BN, 64);
+  if (!B_MN) rc = make_tmap_bf16_2d(&mb, B, N, K, ldb, MC ? BN / 2 : BN, 64);
   else       rc = make_tmap_bf16_2d(&mb, B, K, N, ldb, kBK, 64);
   if (rc) return rc;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MC>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     OTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, M, N, K, ep);
+  const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + BN - 1) / BN;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  if (MC) {
+    const int pairs = ((tiles_m + 1) / 2) * tiles_n;
+    const int max_pairs = sm_count() / 2;
+    cfg.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  } else {
+    const int tiles = tiles_m * tiles_n;
+    cfg.gridDim = dim3(tiles < sm_count() ? tiles : sm_count());
+  }
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  OTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, ep));
   count_launch();
-  OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
 }
 
@@ -331,24 +370,33 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   ep.alpha = e->alpha;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  // Tile-N choice: 256-wide tiles unless that leaves most SMs idle.
-  const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
+  // Tile-N choice: 256-wide tiles unless that leaves most SMs idle.  CTA-pair multicast (MC) when there are at
+  // least two row tiles and enough pairs to fill the chip (otherwise single CTAs spread wider).
+  const int tiles_m = (M + kBM - 1) / kBM;
+  const int tiles256 = tiles_m * ((N + 255) / 256);
   const bool bn128 = (N <= 128) || (tiles256 < sm_count() && N > 128);
+  const int tiles = bn128 ? tiles_m * ((N + 127) / 128) : tiles256;
+  static const bool mc_off = (getenv("OTB_GEMM_NO_MCAST") != nullptr);
+  const bool mc = !mc_off && tiles_m >= 2 && (tiles_m % 2 == 0 || tiles_m >= 9) && tiles >= sm_count();
   const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+#define OTB_GEMM_CASE(BN_, A_, B_)                                                                   \
+  return mc ? launch_gemm<BN_, A_, B_, true>(A, lda, B, ldb, M, N, K, ep, st)                         \
+            : launch_gemm<BN_, A_, B_, false>(A, lda, B, ldb, M, N, K, ep, st)
   if (bn128) {
     switch (sel) {
-      case 0: return launch_gemm<128, false, false>(A, lda, B, ldb, M, N, K, ep, st);
-      case 1: return launch_gemm<128, false, true>(A, lda, B, ldb, M, N, K, ep, st);
-      case 3: return launch_gemm<128, true, true>(A, lda, B, ldb, M, N, K, ep, st);
+      case 0: OTB_GEMM_CASE(128, false, false);
+      case 1: OTB_GEMM_CASE(128, false, true);
+      case 3: OTB_GEMM_CASE(128, true, true);
       default: break;
     }
   } else {
     switch (sel) {
-      case 0: return launch_gemm<256, false, false>(A, lda, B, ldb, M, N, K, ep, st);
-      case 1: return launch_gemm<256, false, true>(A, lda, B, ldb, M, N, K, ep, st);
-      case 3: return launch_gemm<256, true, true>(A, lda, B, ldb, M, N, K, ep, st);
+      case 0: OTB_GEMM_CASE(256, false, false);
+      case 1: OTB_GEMM_CASE(256, false, true);
+      case 3: OTB_GEMM_CASE(256, true, true);
       default: break;
     }
   }
+#undef OTB_GEMM_CASE
   return set_error(OTB_ERR_UNSUPPORTED, "otb_gemm_bf16: layout (A MN-major, B K-major) not instantiated");
 }
