@@ -38,6 +38,7 @@ struct GemmEpi {
   long long ld_out, ld_aux_in, ld_aux_out, ld_res;
   int act, scale_tanh, out_fp32, accumulate;
   float alpha;
+  int res_fp32;   // residual is fp32 [M][N] (fp32-grade parity path)
 };
 
 template <int BN>
@@ -204,7 +205,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint4 res[4], aux[4];
         float4 old[8];
         if (act_chunk) {
-          if (ep.residual != nullptr) {
+          if (ep.residual != nullptr && !ep.res_fp32) {
             const uint4* pr = reinterpret_cast<const uint4*>(ep.residual + lrow * ep.ld_res + colbase);
 #pragma unroll
             for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) res[g] = __ldg(pr + g);
@@ -260,7 +261,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= scale;
-            if (ep.residual != nullptr) {
+            if (ep.residual != nullptr && ep.res_fp32) {
+              const float* pr = reinterpret_cast<const float*>(ep.residual) + lrow * ep.ld_res + col;
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(pr)), r1 = __ldg(reinterpret_cast<const float4*>(pr + 4));
+              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+              v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+            } else if (ep.residual != nullptr) {
               const float2 a0 = unpack_bf16x2(res[g].x), a1 = unpack_bf16x2(res[g].y), a2 = unpack_bf16x2(res[g].z),
                            a3 = unpack_bf16x2(res[g].w);
               v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
@@ -368,6 +374,8 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   ep.ld_out = e->ld_out; ep.ld_aux_in = e->ld_aux_in; ep.ld_aux_out = e->ld_aux_out; ep.ld_res = e->ld_res;
   ep.act = e->act; ep.scale_tanh = e->scale_tanh; ep.out_fp32 = e->out_fp32; ep.accumulate = e->accumulate;
   ep.alpha = e->alpha;
+  ep.res_fp32 = e->res_fp32;
+  OTB_CHECK_ARG(!e->res_fp32 || e->out_fp32, "otb_gemm_bf16: fp32 residual requires fp32 output");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // Tile-N choice: 256-wide tiles unless that leaves most SMs idle.  CTA-pair multicast (MC) when there are at

@@ -73,7 +73,7 @@ typedef struct otb_gemm_epilogue {
   int32_t out_fp32;
   int32_t accumulate;
   float alpha;
-  int32_t _pad;
+  int32_t res_fp32; /* residual is fp32 [M][N] instead of bf16 (fp32-grade parity path; needs out_fp32) */
 } otb_gemm_epilogue;
 
 int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb, int M,
@@ -164,6 +164,23 @@ int otb_gate_grad(const void* dy, const void* a, int64_t n, const float* gate, f
                   float* ws, void* stream);
 /* loss = mean(x^2) (fp32, *loss written), dx = 2 x / n  — the M1 harness loss. */
 int otb_sqmean_loss(const void* x, int64_t n, float* loss, void* dx, float* ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fp32-grade forward path (parity mode, csrc/otb_fp32.cu): reproduces the reference's fp32 forward within
+ * 1e-3 rel / 1e-5 abs.  GEMMs stay on otb_gemm_bf16: x = x0+x1+x2 (bf16 terms), six cross products as one
+ * GEMM over K' = 6K.  otb_split3_concat builds the [rows][6K] operand: pattern 0 = [x0 x0 x1 x1 x0 x2]
+ * (A side), pattern 1 = [y0 y1 y0 y1 y2 y0] (B side).  otb_attn_fwd_f32 takes the same descriptor with fp32
+ * q/kv/out matrices (lse ignored).
+ * ------------------------------------------------------------------------------------------- */
+int otb_split3_concat(const float* src, int64_t ld, int rows, int K, int pattern, void* dst, void* stream);
+int otb_layernorm_fwd_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float* y, int64_t ldy,
+                          int rows, int D, float eps, void* stream);
+int otb_add_rowbias_f32(const float* x, const float* bias, int div, int mod, float* out, int rows, int D,
+                        void* stream);
+int otb_attn_fwd_f32(const otb_attn_desc* d, void* stream);
+/* out = act(acc + bias[n]) * gate + residual   (fp32 [M][N] contiguous; same order as the fused GEMM epilogue) */
+int otb_epilogue_f32(const float* acc, const float* bias, int act, const float* scale_ptr, int scale_tanh,
+                     const float* residual, float* out, int M, int N, void* stream);
 
 /* CLIP embeddings (xformers_model/clip.py:73-81): */
 /* im2col of non-overlapping patches: pixels [N][3][H][W] (fp32 if pix_fp32 else bf16) ->

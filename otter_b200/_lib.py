@@ -20,7 +20,7 @@ class GemmEpilogue(C.Structure):
         ("residual", C.c_void_p), ("out", C.c_void_p),
         ("ld_out", C.c_int64), ("ld_aux_in", C.c_int64), ("ld_aux_out", C.c_int64), ("ld_res", C.c_int64),
         ("act", C.c_int32), ("scale_tanh", C.c_int32), ("out_fp32", C.c_int32), ("accumulate", C.c_int32),
-        ("alpha", C.c_float), ("_pad", C.c_int32),
+        ("alpha", C.c_float), ("res_fp32", C.c_int32),
     ]
 
 
@@ -72,6 +72,11 @@ SIGNATURES = {
     "otb_dot_blocks": (_I, []),
     "otb_gate_grad": (_I, [_VP, _VP, _I64, _VP, _VP, _I, _VP, _VP]),
     "otb_sqmean_loss": (_I, [_VP, _I64, _VP, _VP, _VP, _VP]),
+    "otb_split3_concat": (_I, [_VP, _I64, _I, _I, _I, _VP, _VP]),
+    "otb_layernorm_fwd_f32": (_I, [_VP, _I64, _VP, _VP, _VP, _I64, _I, _I, _F, _VP]),
+    "otb_add_rowbias_f32": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP]),
+    "otb_attn_fwd_f32": (_I, [C.POINTER(AttnDesc), _VP]),
+    "otb_epilogue_f32": (_I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _I, _I, _VP]),
     "otb_im2col_patches": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _I, _VP]),
     "otb_clip_assemble": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "otb_media_from_clip": (_I, [_VP, _VP, _I, _VP, _I, _I, _I, _VP]),

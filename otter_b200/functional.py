@@ -32,9 +32,9 @@ def _req(t, dtype=None, name="tensor"):
     return t
 
 
-def _mat(t, name="matrix"):
+def _mat(t, name="matrix", dtype=BF16):
     """2-D view [rows, cols] with unit column stride (leading dims flattened when contiguous)."""
-    _req(t, BF16, name)
+    _req(t, dtype, name)
     if t.dim() == 2:
         return t
     return t.reshape(-1, t.shape[-1])
@@ -53,7 +53,7 @@ def set_gemm_profiler(sink):
 
 
 def _gemm_raw(A, a_mn, lda, B, b_mn, ldb, M, N, K, out, *, bias=None, act=0, aux_out=None, aux_in=None,
-              scale_ptr=None, scale_tanh=False, alpha=1.0, residual=None, accumulate=False):
+              scale_ptr=None, scale_tanh=False, alpha=1.0, residual=None, accumulate=False, res_fp32=False):
     lib = _lib.load()
     e = GemmEpilogue()
     e.bias = _p(bias)
@@ -71,6 +71,7 @@ def _gemm_raw(A, a_mn, lda, B, b_mn, ldb, M, N, K, out, *, bias=None, act=0, aux
     e.out_fp32 = 1 if out.dtype == torch.float32 else 0
     e.accumulate = 1 if accumulate else 0
     e.alpha = alpha
+    e.res_fp32 = 1 if res_fp32 else 0
     if _GEMM_PROF is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -164,10 +165,10 @@ class AttnSpec:
     """Where Q / K / V / O live inside their 2-D buffers (see otb_attn_desc)."""
 
     def __init__(self, q, q_col0, kv1, k1_col0, v1_col0, P, H, Sq, Sk1, scale, kv2=None, k2_col0=0, v2_col0=0, Sk2=0,
-                 text_time=None, n_per_media=0, T_img=0):
-        self.q, self.q_col0 = _mat(q, "q"), q_col0
-        self.kv1, self.k1_col0, self.v1_col0 = _mat(kv1, "kv1"), k1_col0, v1_col0
-        self.kv2 = _mat(kv2, "kv2") if kv2 is not None else None
+                 text_time=None, n_per_media=0, T_img=0, dtype=BF16):
+        self.q, self.q_col0 = _mat(q, "q", dtype), q_col0
+        self.kv1, self.k1_col0, self.v1_col0 = _mat(kv1, "kv1", dtype), k1_col0, v1_col0
+        self.kv2 = _mat(kv2, "kv2", dtype) if kv2 is not None else None
         self.k2_col0, self.v2_col0 = k2_col0, v2_col0
         self.P, self.H, self.Sq, self.Sk1, self.Sk2, self.scale = P, H, Sq, Sk1, Sk2, scale
         self.text_time, self.n_per_media, self.T_img = text_time, n_per_media, T_img
@@ -342,6 +343,85 @@ def fuyu_scatter(word, cont, idx, b_off):
     out = torch.empty_like(word)
     check(_lib.load().otb_fuyu_scatter(_p(word.contiguous()), _p(cont.contiguous()), _p(idx.contiguous()),
                                        _p(b_off.contiguous()), _p(out), B, S, D, _stream()), "otb_fuyu_scatter")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32-grade forward path (parity mode; csrc/otb_fp32.cu)
+# ------------------------------------------------------------------------------------------------
+F32_KCHUNK = 512
+
+
+def epilogue_f32(acc, *, bias=None, act=0, scale_ptr=None, scale_tanh=False, residual=None):
+    """fp32 epilogue of the chunked fp32-grade GEMM: act(acc + bias) * gate + residual (otb_epilogue_f32)."""
+    acc = _mat(acc, "acc", torch.float32)
+    M, N = acc.shape
+    out = torch.empty_like(acc)
+    check(_lib.load().otb_epilogue_f32(_p(acc), _p(bias), act, _p(scale_ptr), int(bool(scale_tanh)), _p(residual),
+                                       _p(out), M, N, _stream()), "otb_epilogue_f32")
+    return out
+
+
+def split3_concat(src, pattern):
+    """fp32 [rows, K] -> bf16 [rows, 6K]: three-term bf16 split laid out for the 6-product GEMM."""
+    src = _mat(src, "src", torch.float32)
+    rows, K = src.shape
+    out = torch.empty((rows, 6 * K), device=src.device, dtype=BF16)
+    check(_lib.load().otb_split3_concat(_p(src), src.stride(0), rows, K, pattern, _p(out), _stream()), "otb_split3_concat")
+    return out
+
+
+def linear_f32(x, w6, N, *, bias=None, act=0, scale_ptr=None, scale_tanh=False, residual=None):
+    """y fp32 [M,N] = epilogue(x fp32 [M,K] @ W^T) with fp32-grade accuracy; w6 = split3_concat(W, 1)."""
+    x = _mat(x, "x", torch.float32)
+    M, K = x.shape
+    assert w6.shape == (N, 6 * K), (w6.shape, N, K)
+    a6 = split3_concat(x, 0)
+    out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    if residual is not None:
+        residual = _mat(residual, "residual", torch.float32)
+    # The tensor core adds into its fp32 accumulator with truncation, so a long in-TMEM reduction drifts by
+    # ~(#MMA steps) * 2^-24 of the running sum.  Keep each in-TMEM run short (F32_KCHUNK columns of K') and
+    # carry the running sum in fp32 through the epilogue's round-to-nearest accumulate instead.
+    K6, kc = 6 * K, F32_KCHUNK
+    if K6 <= kc:
+        return _gemm_raw(a6, 0, a6.stride(0), w6, 0, w6.stride(0), M, N, K6, out, bias=bias, act=act,
+                         scale_ptr=scale_ptr, scale_tanh=scale_tanh, residual=residual, res_fp32=residual is not None)
+    nchunk = (K6 + kc - 1) // kc
+    for i in range(nchunk):
+        k0, k1 = i * kc, min(K6, (i + 1) * kc)
+        _gemm_raw(a6[:, k0:k1], 0, a6.stride(0), w6[:, k0:k1], 0, w6.stride(0), M, N, k1 - k0, out,
+                  accumulate=(i > 0))
+    if bias is not None or act or scale_ptr is not None or residual is not None:
+        out = epilogue_f32(out, bias=bias, act=act, scale_ptr=scale_ptr, scale_tanh=scale_tanh, residual=residual)
+    return out
+
+
+def layernorm_fwd_f32(x, gamma, beta, eps=1e-5):
+    x2 = _mat(x, "x", torch.float32)
+    rows, D = x2.shape
+    y = torch.empty((rows, D), device=x.device, dtype=torch.float32)
+    check(_lib.load().otb_layernorm_fwd_f32(_p(x2), x2.stride(0), _p(_req(gamma, torch.float32)),
+                                            _p(_req(beta, torch.float32)), _p(y), y.stride(0), rows, D, eps, _stream()),
+          "otb_layernorm_fwd_f32")
+    return y.view(x.shape)
+
+
+def add_rowbias_f32(x, bias, div, mod):
+    x2 = _mat(x, "x", torch.float32)
+    assert x2.is_contiguous()
+    rows, D = x2.shape
+    out = torch.empty_like(x2)
+    check(_lib.load().otb_add_rowbias_f32(_p(x2), _p(_req(bias, torch.float32)), div, mod, _p(out), rows, D, _stream()),
+          "otb_add_rowbias_f32")
+    return out
+
+
+def attn_fwd_f32(spec):
+    """spec: AttnSpec(dtype=torch.float32) -> fp32 [P*Sq, H*64]."""
+    out = torch.empty((spec.P * spec.Sq, spec.H * 64), device=spec.q.device, dtype=torch.float32)
+    d = spec.desc(out, 0, None)
+    check(_lib.load().otb_attn_fwd_f32(C.byref(d), _stream()), "otb_attn_fwd_f32")
     return out
 
 

@@ -137,6 +137,15 @@ class CLIPVisionModel(nn.Module):
     def forward(self, pixel_values=None, output_attentions=None, output_hidden_states=None, return_dict=None, **kw):
         if pixel_values is None:
             raise ValueError("You have to specify pixel_values")
+        from . import fp32_path
+        if fp32_path.is_fp32():                                        # fp32-grade parity mode (forward only)
+            fp32_path.require_no_grad(pixel_values, *self.parameters())
+            with torch.no_grad():
+                h32 = fp32_path.clip_last_hidden(self, pixel_values)
+                vm = self.vision_model
+                pooled = F.layernorm_fwd_f32(h32[:, 0, :].contiguous(), f32_of(vm.post_layernorm.weight),
+                                             f32_of(vm.post_layernorm.bias), self.config.layer_norm_eps)
+            return CLIPVisionOutput((h32, pooled))
         h = self.last_hidden_bf16(pixel_values)                        # bf16 [N, S, D]
         vm = self.vision_model
         with torch.no_grad():

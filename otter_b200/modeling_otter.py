@@ -15,6 +15,7 @@ from typing import List, Optional
 import torch
 import torch.nn as nn
 
+from . import fp32_path
 from . import functional as F
 from .blocks import (BroadcastRowsFn, GatedCrossAttentionBlockFn, LayerNormFn, MaskedCrossAttentionFn,
                      MediaFromClipFn, PerceiverBlockFn, _as_bf16_2d)
@@ -84,6 +85,10 @@ class OtterPerceiverBlock(nn.Module):
     def forward(self, x: torch.Tensor, latents: torch.Tensor) -> torch.Tensor:
         """x (b, T, n1, D) media features, latents (b, T, n2, D) -> (b, T, n2, D)."""
         b, T, n2, D = latents.shape
+        if fp32_path.is_fp32():
+            fp32_path.require_no_grad(x, latents, *self.parameters())
+            out = fp32_path.perceiver_block(self, fp32_path._f32_2d(x, D), fp32_path._f32_2d(latents, D), b * T)
+            return out.view(b, T, n2, D).to(latents.dtype)
         out = self._apply2d(_as_bf16_2d(x, D), _as_bf16_2d(latents, D), b * T, x.requires_grad)
         return out.view(b, T, n2, D).to(latents.dtype)
 
@@ -113,6 +118,9 @@ class OtterPerceiverResampler(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x (b, T, F, v, D) -> (b, T, n, D)."""
         b, T, Fr, v, D = x.shape
+        if fp32_path.is_fp32():
+            fp32_path.require_no_grad(x, *self.parameters())
+            return fp32_path.resampler_forward(self, x).to(x.dtype)
         media = _as_bf16_2d(x, D)
         if exists(self.frame_embs):                                                    # :224-226
             media = _AddRowBiasFn.apply(media, self.frame_embs, v, Fr)
@@ -156,6 +164,11 @@ class OtterMaskedCrossAttention(nn.Module):
         B, L, D = x.shape
         _, T_img, n = media.shape[:3]
         tt = _text_time_for(media_locations, attend_previous)
+        if fp32_path.is_fp32():
+            fp32_path.require_no_grad(x, media, *self.parameters())
+            out = fp32_path.masked_cross_attention(self, fp32_path._f32_2d(x, D),
+                                                   fp32_path._f32_2d(media, media.shape[-1]), tt, B, L, T_img, n)
+            return out.view(B, L, D).to(x.dtype)
         out = MaskedCrossAttentionFn.apply(_as_bf16_2d(x, D), _as_bf16_2d(media, media.shape[-1]), tt, B, L, T_img, n,
                                            self.heads, self.norm.weight, self.norm.bias, self.to_q.weight,
                                            self.to_kv.weight, self.to_out.weight)
@@ -187,6 +200,11 @@ class OtterGatedCrossAttentionBlock(nn.Module):
         B, L, D = x.shape
         _, T_img, n = media.shape[:3]
         tt = _text_time_for(media_locations, attend_previous)
+        if fp32_path.is_fp32():
+            fp32_path.require_no_grad(x, media, *self.parameters())
+            out = fp32_path.gated_block(self, fp32_path._f32_2d(x, D), fp32_path._f32_2d(media, media.shape[-1]), tt,
+                                        B, L, T_img, n)
+            return out.view(B, L, D).to(x.dtype)
         out = self.forward_2d(_as_bf16_2d(x, D), _as_bf16_2d(media, media.shape[-1]), tt, B, L, T_img, n)
         return out.view(B, L, D).to(x.dtype)
 
@@ -315,6 +333,9 @@ def encode_vision_x(vision_encoder, perceiver, vision_x):
     assert vision_x.ndim == 6, "vision_x should be of shape (b, T_img, F, C, H, W)"
     b, T, Fr = vision_x.shape[:3]
     pixels = vision_x.reshape(b * T * Fr, *vision_x.shape[3:])
+    if fp32_path.is_fp32() and isinstance(vision_encoder, CLIPVisionModel):
+        feats = fp32_path.clip_last_hidden(vision_encoder, pixels)[:, 1:, :]
+        return perceiver(feats.reshape(b, T, Fr, feats.shape[1], feats.shape[2]))
     if isinstance(vision_encoder, CLIPVisionModel):
         hidden = vision_encoder.last_hidden_bf16(pixels)                       # bf16 [bTF, 1+v, D]
         media = MediaFromClipFn.apply(hidden, perceiver.frame_embs, Fr)        # drop CLS (+frame_embs) fused

