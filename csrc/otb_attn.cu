@@ -105,6 +105,7 @@ __device__ __forceinline__ void st_sw128(uint8_t* chunk_base, int r, int c_in_ch
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv1,
                 const __grid_constant__ CUtensorMap map_kv2, AttnParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_q = smem;                        // 16 KB
@@ -129,6 +130,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();   // predecessor grid complete before any global / TMA access
   const uint32_t t_s = tmem;         // S: columns [0,128)
   const uint32_t t_o = tmem + 128;   // O: columns [128,192)
 
@@ -293,6 +295,7 @@ constexpr int kResThreads = 256;
 __global__ void __launch_bounds__(kResThreads)
 attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv1,
                          const __grid_constant__ CUtensorMap map_kv2, AttnParams p, int nt, int tmem_cols) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_q = smem;                              // 16 KB
@@ -323,6 +326,7 @@ attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();   // predecessor grid complete before any global / TMA access
   const uint32_t t_o = tmem + nt * 128;
   const int nt1 = (p.Sk1 + 127) / 128;
 
@@ -504,6 +508,7 @@ __global__ void __launch_bounds__(kAttnThreads)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_kv1, const __grid_constant__ CUtensorMap map_kv2,
                 AttnParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_k = smem;                      // 16 KB  K_j  [128 keys][64 d]
@@ -530,6 +535,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();   // predecessor grid complete before any global / TMA access
   const uint32_t t_s = tmem, t_dp = tmem + 128, t_dv = tmem + 256, t_dk = tmem + 320, t_dq = tmem + 384;
   const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
 
@@ -799,10 +805,10 @@ extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
   if (nt <= 3) {
     const int smem = (1 + 2 * nt + 4) * kTileBytes + 1024 + 2048;
     const int tmem_cols = (nt == 1) ? 256 : 512;
-    attn_fwd_resident_kernel<<<grid, kResThreads, smem, static_cast<cudaStream_t>(stream)>>>(mq, mk1, mk2, p, nt,
-                                                                                             tmem_cols);
+    OTB_CHECK_CUDA(launch_k(attn_fwd_resident_kernel, dim3(grid), dim3(kResThreads), smem, static_cast<cudaStream_t>(stream), mq, mk1, mk2, p, nt,
+                                                                                             tmem_cols));
   } else {
-    attn_fwd_kernel<<<grid, kAttnThreads, kAttnFwdSmem, static_cast<cudaStream_t>(stream)>>>(mq, mk1, mk2, p);
+    OTB_CHECK_CUDA(launch_k(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), kAttnFwdSmem, static_cast<cudaStream_t>(stream), mq, mk1, mk2, p));
   }
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
@@ -839,7 +845,7 @@ extern "C" int otb_attn_bwd(const otb_attn_desc* d, const otb_attn_grads* g, voi
     attr = true;
   }
   dim3 grid(d->H, d->P);
-  attn_bwd_kernel<<<grid, kAttnThreads, kAttnBwdSmem, static_cast<cudaStream_t>(stream)>>>(mq, mdo, mk1, mk2, p);
+  OTB_CHECK_CUDA(launch_k(attn_bwd_kernel, dim3(grid), dim3(kAttnThreads), kAttnBwdSmem, static_cast<cudaStream_t>(stream), mq, mdo, mk1, mk2, p));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;

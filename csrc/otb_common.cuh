@@ -34,6 +34,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: every kernel lets its successor's CTAs start early (launch_dependents) and
+// itself waits for the complete predecessor grid (and its memory) right before the first global access, so
+// prologues (barrier init, TMEM alloc, descriptor prefetch, launch latency) overlap the predecessor's tail.
+// Both are no-ops when the kernel was not launched with the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -19,6 +19,8 @@ __device__ __forceinline__ float warp_sum32(float v) {
 // pattern 0 (A side): [x0 x0 x1 x1 x0 x2]   pattern 1 (B side): [y0 y1 y0 y1 y2 y0]
 __global__ void split3_concat_kernel(const float* __restrict__ src, long long ld, int rows, int K, int pattern,
                                      bf16* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(rows) * K;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -41,6 +43,8 @@ __global__ void split3_concat_kernel(const float* __restrict__ src, long long ld
 __global__ void __launch_bounds__(256)
 ln_fwd_f32_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float* __restrict__ y, long long ldy, int rows, int D, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -57,6 +61,8 @@ ln_fwd_f32_kernel(const float* __restrict__ x, long long ldx, const float* __res
 
 __global__ void add_rowbias_f32_kernel(const float* __restrict__ x, const float* __restrict__ bias, int div, int mod,
                                        float* __restrict__ out, int rows, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(rows) * D;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -69,6 +75,8 @@ __global__ void add_rowbias_f32_kernel(const float* __restrict__ x, const float*
 __global__ void epilogue_f32_kernel(const float* __restrict__ acc, const float* __restrict__ bias, int act,
                                     const float* __restrict__ scale_ptr, int scale_tanh,
                                     const float* __restrict__ residual, float* __restrict__ out, int M, int N) {
+  pdl_launch_dependents();
+  pdl_wait();
   float scale = 1.0f;
   if (scale_ptr != nullptr) scale = scale_tanh ? tanhf(*scale_ptr) : *scale_ptr;
   const long long total = static_cast<long long>(M) * N;
@@ -93,6 +101,8 @@ struct AttnF32 {
   float scale;
 };
 __global__ void __launch_bounds__(64) attn_fwd_f32_kernel(AttnF32 p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * 64 + threadIdx.x, h = blockIdx.y, prob = blockIdx.z;
   if (row >= p.Sq) return;
   const long long grow = static_cast<long long>(prob) * p.Sq + row;
@@ -164,8 +174,8 @@ using namespace otb;
 extern "C" int otb_split3_concat(const float* src, int64_t ld, int rows, int K, int pattern, void* dst, void* stream) {
   OTB_CHECK_ARG(src && dst && rows > 0 && K > 0 && ld >= K && (pattern == 0 || pattern == 1),
                 "otb_split3_concat: bad argument");
-  split3_concat_kernel<<<grid1d(static_cast<long long>(rows) * K, 256), 256, 0, ST(stream)>>>(
-      src, ld, rows, K, pattern, static_cast<bf16*>(dst));
+  OTB_CHECK_CUDA(launch_k(split3_concat_kernel, dim3(grid1d(static_cast<long long>(rows) * K, 256)), dim3(256), 0, ST(stream), 
+      src, ld, rows, K, pattern, static_cast<bf16*>(dst)));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -173,7 +183,7 @@ extern "C" int otb_split3_concat(const float* src, int64_t ld, int rows, int K, 
 extern "C" int otb_layernorm_fwd_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float* y,
                                      int64_t ldy, int rows, int D, float eps, void* stream) {
   OTB_CHECK_ARG(x && gamma && beta && y && rows > 0 && D > 0, "otb_layernorm_fwd_f32: bad argument");
-  ln_fwd_f32_kernel<<<(rows + 7) / 8, 256, 0, ST(stream)>>>(x, ldx, gamma, beta, y, ldy, rows, D, eps);
+  OTB_CHECK_CUDA(launch_k(ln_fwd_f32_kernel, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), x, ldx, gamma, beta, y, ldy, rows, D, eps));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -181,8 +191,8 @@ extern "C" int otb_layernorm_fwd_f32(const float* x, int64_t ldx, const float* g
 extern "C" int otb_add_rowbias_f32(const float* x, const float* bias, int div, int mod, float* out, int rows, int D,
                                    void* stream) {
   OTB_CHECK_ARG(x && bias && out && div > 0 && mod > 0 && rows > 0 && D > 0, "otb_add_rowbias_f32: bad argument");
-  add_rowbias_f32_kernel<<<grid1d(static_cast<long long>(rows) * D, 256), 256, 0, ST(stream)>>>(x, bias, div, mod, out,
-                                                                                              rows, D);
+  OTB_CHECK_CUDA(launch_k(add_rowbias_f32_kernel, dim3(grid1d(static_cast<long long>(rows) * D, 256)), dim3(256), 0, ST(stream), x, bias, div, mod, out,
+                                                                                              rows, D));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -190,8 +200,8 @@ extern "C" int otb_add_rowbias_f32(const float* x, const float* bias, int div, i
 extern "C" int otb_epilogue_f32(const float* acc, const float* bias, int act, const float* scale_ptr, int scale_tanh,
                                 const float* residual, float* out, int M, int N, void* stream) {
   OTB_CHECK_ARG(acc && out && M > 0 && N > 0 && act >= 0 && act <= 2, "otb_epilogue_f32: bad argument");
-  epilogue_f32_kernel<<<grid1d(static_cast<long long>(M) * N, 256), 256, 0, ST(stream)>>>(acc, bias, act, scale_ptr,
-                                                                                        scale_tanh, residual, out, M, N);
+  OTB_CHECK_CUDA(launch_k(epilogue_f32_kernel, dim3(grid1d(static_cast<long long>(M) * N, 256)), dim3(256), 0, ST(stream), acc, bias, act, scale_ptr,
+                                                                                        scale_tanh, residual, out, M, N));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -210,7 +220,7 @@ extern "C" int otb_attn_fwd_f32(const otb_attn_desc* d, void* stream) {
   p.o_col0 = d->out_col0; p.n_per_media = d->n_per_media; p.T_img = d->T_img;
   p.P = d->P; p.H = d->H; p.Sq = d->Sq; p.Sk1 = d->Sk1; p.Sk2 = d->Sk2; p.scale = d->scale;
   dim3 grid((d->Sq + 63) / 64, d->H, d->P);
-  attn_fwd_f32_kernel<<<grid, 64, 0, ST(stream)>>>(p);
+  OTB_CHECK_CUDA(launch_k(attn_fwd_f32_kernel, dim3(grid), dim3(64), 0, ST(stream), p));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;

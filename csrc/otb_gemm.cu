@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
                  int K, GemmEpi ep) {
   using Cfg = GemmCfg<BN>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -99,6 +100,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if constexpr (MC) cluster_sync_all();       // peer barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // predecessor grid complete before any global / TMA access
 
   if (warp == 10 && lane == 0) {
     // ===================== TMA producer =====================
@@ -324,18 +326,26 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   }
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + BN - 1) / BN;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
+  if (pdl_enabled()) {
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
   if (MC) {
     const int pairs = ((tiles_m + 1) / 2) * tiles_n;
     const int max_pairs = sm_count() / 2;
     cfg.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = 2; attr[nattr].val.clusterDim.y = 1; attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
   } else {
     const int tiles = tiles_m * tiles_n;
     cfg.gridDim = dim3(tiles < sm_count() ? tiles : sm_count());
   }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 namespace otb {
@@ -57,6 +58,11 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
     return set_error(OTB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
   return OTB_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("OTB_PDL"); return (e && e[0] == '1'); }();
+  return on;
 }
 
 int sm_count() {

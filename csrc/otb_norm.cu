@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ gamma,
               const float* __restrict__ beta, bf16* __restrict__ y, long long ldy, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, int rows, int D, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -74,6 +76,8 @@ ln_bwd_dx_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __rest
                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                  const bf16* __restrict__ add, long long ldadd, bf16* __restrict__ dx, long long lddx, int rows,
                  int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -122,6 +126,8 @@ __global__ void __launch_bounds__(256)
 ln_bwd_param_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ x, long long ldx,
                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ ws, int rows,
                     int D, int chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sg[8][64], sb[8][64];
   const int col = blockIdx.x * 64 + threadIdx.x * 2;
   const int chunk = blockIdx.y;
@@ -152,6 +158,8 @@ ln_bwd_param_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __r
 }
 __global__ void ln_bwd_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int D, int chunks, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
   float g = 0.f, b = 0.f;
@@ -168,6 +176,8 @@ __global__ void ln_bwd_finalize_kernel(const float* __restrict__ ws, float* __re
 // ------------------------------------------------------------------------------------------------
 __global__ void text_time_kernel(const uint8_t* __restrict__ loc, int B, int L, int attend_previous,
                                  int* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const uint8_t* l = loc + static_cast<long long>(b) * L;
@@ -192,6 +202,8 @@ __global__ void text_time_kernel(const uint8_t* __restrict__ loc, int B, int L, 
 // casts / broadcasts / reductions
 // ------------------------------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -204,6 +216,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
   }
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -218,6 +232,8 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
 }
 __global__ void bcast_rows_kernel(const float* __restrict__ src, int div, int mod, bf16* __restrict__ out, int rows,
                                   int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = D >> 3;
   const long long total = static_cast<long long>(rows) * nvec;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -233,6 +249,8 @@ __global__ void bcast_rows_kernel(const float* __restrict__ src, int div, int mo
 // out[r,:] = x[r,:] + bias[(r/div)%mod,:]   (frame_embs broadcast add, modeling_otter.py:224-226)
 __global__ void add_rowbias_kernel(const bf16* __restrict__ x, const float* __restrict__ bias, int div, int mod,
                                    bf16* __restrict__ out, int rows, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = D >> 3;
   const long long total = static_cast<long long>(rows) * nvec;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -250,6 +268,8 @@ __global__ void add_rowbias_kernel(const bf16* __restrict__ x, const float* __re
 __global__ void __launch_bounds__(256)
 grouped_colsum_kernel(const bf16* __restrict__ x, long long ldx, int rows, int D, int div, int mod,
                       float* __restrict__ out, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s[8][64];
   const int col = blockIdx.x * 64 + threadIdx.x * 2;
   const int g = blockIdx.y;
@@ -285,6 +305,8 @@ grouped_colsum_kernel(const bf16* __restrict__ x, long long ldx, int rows, int D
 constexpr int kDotBlocks = 592;  // 4 per SM
 __global__ void __launch_bounds__(256)
 dot_partial_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long long n, float* __restrict__ ws) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   float acc = 0.f;
   const long long nvec = n >> 3;
@@ -310,9 +332,14 @@ dot_partial_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, long 
 }
 __global__ void gate_grad_finalize_kernel(const float* __restrict__ ws, int nblk, const float* __restrict__ gate,
                                           float* __restrict__ dgate, int accumulate) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < nblk; ++i) t += ws[i];
+  pdl_launch_dependents();
+  pdl_wait();
+  // one warp, fixed summation order (lane-strided partials, then a shuffle tree) -> deterministic
+  double t = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += 32) t += ws[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (threadIdx.x == 0) {
     const float th = tanhf(*gate);
     const float g = (1.0f - th * th) * static_cast<float>(t);
     *dgate = (accumulate ? *dgate : 0.f) + g;
@@ -320,6 +347,8 @@ __global__ void gate_grad_finalize_kernel(const float* __restrict__ ws, int nblk
 }
 __global__ void __launch_bounds__(256)
 sqmean_partial_kernel(const bf16* __restrict__ x, long long n, float* __restrict__ ws, bf16* __restrict__ dx) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   float acc = 0.f;
   const float gscale = 2.0f / static_cast<float>(n);
@@ -343,11 +372,13 @@ sqmean_partial_kernel(const bf16* __restrict__ x, long long n, float* __restrict
   }
 }
 __global__ void sqmean_finalize_kernel(const float* __restrict__ ws, int nblk, long long n, float* __restrict__ loss) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < nblk; ++i) t += ws[i];
-    *loss = static_cast<float>(t / static_cast<double>(n));
-  }
+  pdl_launch_dependents();
+  pdl_wait();
+  double t = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += 32) t += ws[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (threadIdx.x == 0) *loss = static_cast<float>(t / static_cast<double>(n));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -356,6 +387,8 @@ __global__ void sqmean_finalize_kernel(const float* __restrict__ ws, int nblk, l
 template <bool kF32>
 __global__ void im2col_kernel(const void* __restrict__ pixels, int N, int H, int W, int patch, bf16* __restrict__ out,
                               int Kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int gw = W / patch, gh = H / patch;
   const int K = 3 * patch * patch;
   const long long total = static_cast<long long>(N) * gh * gw * Kpad;
@@ -376,6 +409,8 @@ __global__ void im2col_kernel(const void* __restrict__ pixels, int N, int H, int
 }
 __global__ void clip_assemble_kernel(const bf16* __restrict__ patch_emb, const float* __restrict__ cls,
                                      const float* __restrict__ pos, bf16* __restrict__ out, int N, int np, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = D >> 3;
   const long long total = static_cast<long long>(N) * (np + 1) * nvec;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -399,6 +434,8 @@ __global__ void clip_assemble_kernel(const bf16* __restrict__ patch_emb, const f
 }
 __global__ void media_from_clip_kernel(const bf16* __restrict__ hidden, const float* __restrict__ frame_embs, int F,
                                        bf16* __restrict__ out, int n_img, int v_tok, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = D >> 3;
   const long long total = static_cast<long long>(n_img) * v_tok * nvec;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -420,6 +457,8 @@ __global__ void media_from_clip_kernel(const bf16* __restrict__ hidden, const fl
 __global__ void fuyu_scatter_kernel(const bf16* __restrict__ word, const bf16* __restrict__ cont,
                                     const long long* __restrict__ idx, const long long* __restrict__ b_off,
                                     bf16* __restrict__ out, int B, int S, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = D >> 3;
   const long long total = static_cast<long long>(B) * S * nvec;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -451,8 +490,8 @@ extern "C" int otb_layernorm_fwd(const void* x, int64_t ldx, const float* gamma,
                                  int64_t ldy, float* mean, float* rstd, int rows, int D, float eps, void* stream) {
   OTB_CHECK_ARG(x && gamma && beta && y && rows > 0 && D > 0, "otb_layernorm_fwd: bad argument");
   OTB_CHECK_ARG(D % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "otb_layernorm_fwd: D/ld must be multiples of 8");
-  ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), ldx, gamma, beta,
-                                                          static_cast<bf16*>(y), ldy, mean, rstd, rows, D, eps);
+  OTB_CHECK_CUDA(launch_k(ln_fwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), static_cast<const bf16*>(x), ldx, gamma, beta,
+                                                          static_cast<bf16*>(y), ldy, mean, rstd, rows, D, eps));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -474,19 +513,19 @@ extern "C" int otb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, in
   OTB_CHECK_ARG(D % 8 == 0 && lddy % 8 == 0 && ldx % 8 == 0, "otb_layernorm_bwd: D/ld must be multiples of 8");
   if (dx != nullptr) {
     OTB_CHECK_ARG(lddx % 8 == 0 && (add == nullptr || ldadd % 8 == 0), "otb_layernorm_bwd: bad ld");
-    ln_bwd_dx_kernel<<<(rows + 7) / 8, 256, 0, ST(stream)>>>(
+    OTB_CHECK_CUDA(launch_k(ln_bwd_dx_kernel, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 
         static_cast<const bf16*>(dy), lddy, static_cast<const bf16*>(x), ldx, mean, rstd, gamma,
-        static_cast<const bf16*>(add), ldadd, static_cast<bf16*>(dx), lddx, rows, D);
+        static_cast<const bf16*>(add), ldadd, static_cast<bf16*>(dx), lddx, rows, D));
     count_launch();
   }
   if (dgamma != nullptr || dbeta != nullptr) {
     OTB_CHECK_ARG(ws != nullptr, "otb_layernorm_bwd: workspace required for parameter gradients");
     const int chunks = otb_ln_chunks(rows, D);
     dim3 grid((D + 63) / 64, chunks), block(32, 8);
-    ln_bwd_param_kernel<<<grid, block, 0, ST(stream)>>>(static_cast<const bf16*>(dy), lddy,
+    OTB_CHECK_CUDA(launch_k(ln_bwd_param_kernel, dim3(grid), dim3(block), 0, ST(stream), static_cast<const bf16*>(dy), lddy,
                                                           static_cast<const bf16*>(x), ldx, mean, rstd, ws, rows, D,
-                                                          chunks);
-    ln_bwd_finalize_kernel<<<(D + 255) / 256, 256, 0, ST(stream)>>>(ws, dgamma, dbeta, D, chunks, accumulate);
+                                                          chunks));
+    OTB_CHECK_CUDA(launch_k(ln_bwd_finalize_kernel, dim3((D + 255) / 256), dim3(256), 0, ST(stream), ws, dgamma, dbeta, D, chunks, accumulate));
     count_launch(2);
   }
   OTB_CHECK_CUDA(cudaGetLastError());
@@ -496,7 +535,7 @@ extern "C" int otb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, in
 extern "C" int otb_text_time(const uint8_t* media_locations, int B, int L, int attend_previous, int32_t* text_time,
                              void* stream) {
   OTB_CHECK_ARG(media_locations && text_time && B > 0 && L > 0, "otb_text_time: bad argument");
-  text_time_kernel<<<(B + 63) / 64, 64, 0, ST(stream)>>>(media_locations, B, L, attend_previous, text_time);
+  OTB_CHECK_CUDA(launch_k(text_time_kernel, dim3((B + 63) / 64), dim3(64), 0, ST(stream), media_locations, B, L, attend_previous, text_time));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -506,7 +545,7 @@ extern "C" int otb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* s
   OTB_CHECK_ARG(src && dst && n > 0, "otb_cast_f32_bf16: bad argument");
   OTB_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
                 "otb_cast_f32_bf16: pointers must be 16-byte aligned");
-  cast_f32_bf16_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, ST(stream)>>>(src, static_cast<bf16*>(dst), n);
+  OTB_CHECK_CUDA(launch_k(cast_f32_bf16_kernel, dim3(grid_for((n + 7) / 8, 256)), dim3(256), 0, ST(stream), src, static_cast<bf16*>(dst), n));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -515,15 +554,15 @@ extern "C" int otb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* s
   OTB_CHECK_ARG(src && dst && n > 0, "otb_cast_bf16_f32: bad argument");
   OTB_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
                 "otb_cast_bf16_f32: pointers must be 16-byte aligned");
-  cast_bf16_f32_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, ST(stream)>>>(static_cast<const bf16*>(src), dst, n);
+  OTB_CHECK_CUDA(launch_k(cast_bf16_f32_kernel, dim3(grid_for((n + 7) / 8, 256)), dim3(256), 0, ST(stream), static_cast<const bf16*>(src), dst, n));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
 }
 extern "C" int otb_bcast_rows(const float* src, int div, int mod, void* out, int rows, int D, void* stream) {
   OTB_CHECK_ARG(src && out && div > 0 && mod > 0 && rows > 0 && D % 8 == 0, "otb_bcast_rows: bad argument");
-  bcast_rows_kernel<<<grid_for(static_cast<long long>(rows) * (D / 8), 256), 256, 0, ST(stream)>>>(
-      src, div, mod, static_cast<bf16*>(out), rows, D);
+  OTB_CHECK_CUDA(launch_k(bcast_rows_kernel, dim3(grid_for(static_cast<long long>(rows) * (D / 8), 256)), dim3(256), 0, ST(stream), 
+      src, div, mod, static_cast<bf16*>(out), rows, D));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -531,8 +570,8 @@ extern "C" int otb_bcast_rows(const float* src, int div, int mod, void* out, int
 extern "C" int otb_add_rowbias(const void* x, const float* bias, int div, int mod, void* out, int rows, int D,
                                void* stream) {
   OTB_CHECK_ARG(x && bias && out && div > 0 && mod > 0 && rows > 0 && D % 8 == 0, "otb_add_rowbias: bad argument");
-  add_rowbias_kernel<<<grid_for(static_cast<long long>(rows) * (D / 8), 256), 256, 0, ST(stream)>>>(
-      static_cast<const bf16*>(x), bias, div, mod, static_cast<bf16*>(out), rows, D);
+  OTB_CHECK_CUDA(launch_k(add_rowbias_kernel, dim3(grid_for(static_cast<long long>(rows) * (D / 8), 256)), dim3(256), 0, ST(stream), 
+      static_cast<const bf16*>(x), bias, div, mod, static_cast<bf16*>(out), rows, D));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -542,8 +581,8 @@ extern "C" int otb_grouped_colsum(const void* x, int64_t ldx, int rows, int D, i
   OTB_CHECK_ARG(x && out && div > 0 && mod > 0 && rows > 0 && D % 2 == 0 && ldx % 2 == 0,
                 "otb_grouped_colsum: bad argument");
   dim3 grid((D + 63) / 64, mod), block(32, 8);
-  grouped_colsum_kernel<<<grid, block, 0, ST(stream)>>>(static_cast<const bf16*>(x), ldx, rows, D, div, mod, out,
-                                                          accumulate);
+  OTB_CHECK_CUDA(launch_k(grouped_colsum_kernel, dim3(grid), dim3(block), 0, ST(stream), static_cast<const bf16*>(x), ldx, rows, D, div, mod, out,
+                                                          accumulate));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -552,18 +591,18 @@ extern "C" int otb_dot_blocks(void) { return kDotBlocks; }
 extern "C" int otb_gate_grad(const void* dy, const void* a, int64_t n, const float* gate, float* dgate,
                              int accumulate, float* ws, void* stream) {
   OTB_CHECK_ARG(dy && a && gate && dgate && ws && n > 0, "otb_gate_grad: bad argument");
-  dot_partial_kernel<<<kDotBlocks, 256, 0, ST(stream)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(a), n,
-                                                           ws);
-  gate_grad_finalize_kernel<<<1, 32, 0, ST(stream)>>>(ws, kDotBlocks, gate, dgate, accumulate);
+  OTB_CHECK_CUDA(launch_k(dot_partial_kernel, dim3(kDotBlocks), dim3(256), 0, ST(stream), static_cast<const bf16*>(dy), static_cast<const bf16*>(a), n,
+                                                           ws));
+  OTB_CHECK_CUDA(launch_k(gate_grad_finalize_kernel, dim3(1), dim3(32), 0, ST(stream), ws, kDotBlocks, gate, dgate, accumulate));
   count_launch(2);
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
 }
 extern "C" int otb_sqmean_loss(const void* x, int64_t n, float* loss, void* dx, float* ws, void* stream) {
   OTB_CHECK_ARG(x && loss && ws && n > 0 && n % 8 == 0, "otb_sqmean_loss: bad argument (n %% 8 == 0 required)");
-  sqmean_partial_kernel<<<kDotBlocks, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), n, ws,
-                                                              static_cast<bf16*>(dx));
-  sqmean_finalize_kernel<<<1, 32, 0, ST(stream)>>>(ws, kDotBlocks, n, loss);
+  OTB_CHECK_CUDA(launch_k(sqmean_partial_kernel, dim3(kDotBlocks), dim3(256), 0, ST(stream), static_cast<const bf16*>(x), n, ws,
+                                                              static_cast<bf16*>(dx)));
+  OTB_CHECK_CUDA(launch_k(sqmean_finalize_kernel, dim3(1), dim3(32), 0, ST(stream), ws, kDotBlocks, n, loss));
   count_launch(2);
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -574,9 +613,9 @@ extern "C" int otb_im2col_patches(const void* pixels, int pix_fp32, int N, int H
                 "otb_im2col_patches: bad argument");
   const long long total = static_cast<long long>(N) * (H / patch) * (W / patch) * Kpad;
   if (pix_fp32)
-    im2col_kernel<true><<<grid_for(total, 256), 256, 0, ST(stream)>>>(pixels, N, H, W, patch, static_cast<bf16*>(out), Kpad);
+    OTB_CHECK_CUDA(launch_k(im2col_kernel<true>, dim3(grid_for(total, 256)), dim3(256), 0, ST(stream), pixels, N, H, W, patch, static_cast<bf16*>(out), Kpad));
   else
-    im2col_kernel<false><<<grid_for(total, 256), 256, 0, ST(stream)>>>(pixels, N, H, W, patch, static_cast<bf16*>(out), Kpad);
+    OTB_CHECK_CUDA(launch_k(im2col_kernel<false>, dim3(grid_for(total, 256)), dim3(256), 0, ST(stream), pixels, N, H, W, patch, static_cast<bf16*>(out), Kpad));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -584,8 +623,8 @@ extern "C" int otb_im2col_patches(const void* pixels, int pix_fp32, int N, int H
 extern "C" int otb_clip_assemble(const void* patch_emb, const float* cls, const float* pos, void* out, int N, int np,
                                  int D, void* stream) {
   OTB_CHECK_ARG(patch_emb && cls && pos && out && N > 0 && np > 0 && D % 8 == 0, "otb_clip_assemble: bad argument");
-  clip_assemble_kernel<<<grid_for(static_cast<long long>(N) * (np + 1) * (D / 8), 256), 256, 0, ST(stream)>>>(
-      static_cast<const bf16*>(patch_emb), cls, pos, static_cast<bf16*>(out), N, np, D);
+  OTB_CHECK_CUDA(launch_k(clip_assemble_kernel, dim3(grid_for(static_cast<long long>(N) * (np + 1) * (D / 8), 256)), dim3(256), 0, ST(stream), 
+      static_cast<const bf16*>(patch_emb), cls, pos, static_cast<bf16*>(out), N, np, D));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -593,8 +632,8 @@ extern "C" int otb_clip_assemble(const void* patch_emb, const float* cls, const 
 extern "C" int otb_media_from_clip(const void* hidden, const float* frame_embs, int F, void* out, int n_img, int v,
                                    int D, void* stream) {
   OTB_CHECK_ARG(hidden && out && n_img > 0 && v > 0 && D % 8 == 0 && F > 0, "otb_media_from_clip: bad argument");
-  media_from_clip_kernel<<<grid_for(static_cast<long long>(n_img) * v * (D / 8), 256), 256, 0, ST(stream)>>>(
-      static_cast<const bf16*>(hidden), frame_embs, F, static_cast<bf16*>(out), n_img, v, D);
+  OTB_CHECK_CUDA(launch_k(media_from_clip_kernel, dim3(grid_for(static_cast<long long>(n_img) * v * (D / 8), 256)), dim3(256), 0, ST(stream), 
+      static_cast<const bf16*>(hidden), frame_embs, F, static_cast<bf16*>(out), n_img, v, D));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
@@ -602,9 +641,9 @@ extern "C" int otb_media_from_clip(const void* hidden, const float* frame_embs, 
 extern "C" int otb_fuyu_scatter(const void* word, const void* cont, const int64_t* idx, const int64_t* b_off,
                                 void* out, int B, int S, int D, void* stream) {
   OTB_CHECK_ARG(word && cont && idx && b_off && out && B > 0 && S > 0 && D % 8 == 0, "otb_fuyu_scatter: bad argument");
-  fuyu_scatter_kernel<<<grid_for(static_cast<long long>(B) * S * (D / 8), 256), 256, 0, ST(stream)>>>(
+  OTB_CHECK_CUDA(launch_k(fuyu_scatter_kernel, dim3(grid_for(static_cast<long long>(B) * S * (D / 8), 256)), dim3(256), 0, ST(stream), 
       static_cast<const bf16*>(word), static_cast<const bf16*>(cont), reinterpret_cast<const long long*>(idx),
-      reinterpret_cast<const long long*>(b_off), static_cast<bf16*>(out), B, S, D);
+      reinterpret_cast<const long long*>(b_off), static_cast<bf16*>(out), B, S, D));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;
