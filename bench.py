@@ -385,7 +385,7 @@ def run_cuda(args):
 def cpu_port_sample(steps, warmup, batch):
     """Time `steps` M1 steps of the reference math on CPU (fp32, all host threads) at a bounded batch."""
     from oracle import restatement as R
-    cores = min(host_cores(), 64)      # beyond ~64 threads torch's CPU GEMMs stop scaling on this workload
+    cores = host_cores()               # affinity / cgroup quota aware (the GPU box: 128 visible, quota 16)
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(SEED)
     D, Dv = CFG["D"], CFG["vis_dim"]

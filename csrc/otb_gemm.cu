@@ -51,6 +51,109 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// One epilogue warp's share of one 128 x BN accumulator tile: TMEM lane quarter q (32 rows), column half `half`.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, float scale, uint32_t taddr, int m0, int n0, int M,
+                                              int N, int q, int half, int lane) {
+  const int row = m0 + q * 32 + lane;
+  const bool row_ok = row < M;
+  const long long lrow = row;
+#pragma unroll 1
+  for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+    const int colbase = n0 + c * 32;
+    const bool act_chunk = row_ok && colbase < N;
+    // Issue every global read of this 32-column chunk up front (they do not depend on the accumulator):
+    // each thread reads 64 B of its own row, so the loads of a warp are uncoalesced — what matters is
+    // having all of them in flight together instead of one dependent load per 8 columns.
+    uint4 res[4], aux[4];
+    float4 old[8];
+    if (act_chunk) {
+      if (ep.residual != nullptr && !ep.res_fp32) {
+        const uint4* pr = reinterpret_cast<const uint4*>(ep.residual + lrow * ep.ld_res + colbase);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) res[g] = __ldg(pr + g);
+      }
+      if (ep.aux_in != nullptr) {
+        const uint4* pa = reinterpret_cast<const uint4*>(ep.aux_in + lrow * ep.ld_aux_in + colbase);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) aux[g] = __ldg(pa + g);
+      }
+      if (ep.out_fp32 && ep.accumulate) {
+        const float4* po = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ep.out) + lrow * ep.ld_out + colbase);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) if (colbase + g * 4 < N) old[g] = po[g];
+      }
+    }
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    tmem_ld_wait();
+    if (act_chunk) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = colbase + g * 8;
+        if (col >= N) break;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+        if (ep.bias != nullptr) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (ep.aux_out != nullptr) {
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(ep.aux_out + lrow * ep.ld_aux_out + col) = o;
+        }
+        if (ep.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        } else if (ep.act == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
+        }
+        if (ep.aux_in != nullptr) {
+          const float2 a0 = unpack_bf16x2(aux[g].x), a1 = unpack_bf16x2(aux[g].y), a2 = unpack_bf16x2(aux[g].z),
+                       a3 = unpack_bf16x2(aux[g].w);
+          v[0] *= gelu_erf_grad(a0.x); v[1] *= gelu_erf_grad(a0.y);
+          v[2] *= gelu_erf_grad(a1.x); v[3] *= gelu_erf_grad(a1.y);
+          v[4] *= gelu_erf_grad(a2.x); v[5] *= gelu_erf_grad(a2.y);
+          v[6] *= gelu_erf_grad(a3.x); v[7] *= gelu_erf_grad(a3.y);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= scale;
+        if (ep.residual != nullptr && ep.res_fp32) {
+          const float* pr = reinterpret_cast<const float*>(ep.residual) + lrow * ep.ld_res + col;
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(pr)), r1 = __ldg(reinterpret_cast<const float4*>(pr + 4));
+          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+          v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        } else if (ep.residual != nullptr) {
+          const float2 a0 = unpack_bf16x2(res[g].x), a1 = unpack_bf16x2(res[g].y), a2 = unpack_bf16x2(res[g].z),
+                       a3 = unpack_bf16x2(res[g].w);
+          v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
+          v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+        }
+        if (ep.out_fp32) {
+          float* o = reinterpret_cast<float*>(ep.out) + lrow * ep.ld_out + col;
+          float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+          if (ep.accumulate) { o0 = old[2 * g]; o1 = old[2 * g + 1]; }
+          o0.x += v[0]; o0.y += v[1]; o0.z += v[2]; o0.w += v[3];
+          o1.x += v[4]; o1.y += v[5]; o1.z += v[6]; o1.w += v[7];
+          *reinterpret_cast<float4*>(o) = o0;
+          *reinterpret_cast<float4*>(o + 4) = o1;
+        } else {
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + lrow * ep.ld_out + col) = o;
+        }
+      }
+    }
+  }
+}
+
 // MC = true: clusters of 2 CTAs work on two vertically adjacent 128-row tiles of the same BN-wide column block;
 // each CTA fetches half of the shared B tile and TMA-multicasts it to both, which cuts the L2->SM operand
 // traffic per FLOP by a third (the big GEMMs are L2-bandwidth bound at one 128xBN tile per CTA).
@@ -193,104 +296,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int n0 = (t / tiles_m) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      const long long lrow = row;
-#pragma unroll 1
-      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
-        const int colbase = n0 + c * 32;
-        const bool act_chunk = row_ok && colbase < N;
-        // Issue every global read of this 32-column chunk up front (they do not depend on the accumulator):
-        // each thread reads 64 B of its own row, so the loads of a warp are uncoalesced — what matters is
-        // having all of them in flight together instead of one dependent load per 8 columns.
-        uint4 res[4], aux[4];
-        float4 old[8];
-        if (act_chunk) {
-          if (ep.residual != nullptr && !ep.res_fp32) {
-            const uint4* pr = reinterpret_cast<const uint4*>(ep.residual + lrow * ep.ld_res + colbase);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) res[g] = __ldg(pr + g);
-          }
-          if (ep.aux_in != nullptr) {
-            const uint4* pa = reinterpret_cast<const uint4*>(ep.aux_in + lrow * ep.ld_aux_in + colbase);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) aux[g] = __ldg(pa + g);
-          }
-          if (ep.out_fp32 && ep.accumulate) {
-            const float4* po = reinterpret_cast<const float4*>(reinterpret_cast<float*>(ep.out) + lrow * ep.ld_out + colbase);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) if (colbase + g * 4 < N) old[g] = po[g];
-          }
-        }
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (act_chunk) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = colbase + g * 8;
-            if (col >= N) break;
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-            if (ep.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (ep.aux_out != nullptr) {
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(ep.aux_out + lrow * ep.ld_aux_out + col) = o;
-            }
-            if (ep.act == 1) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
-            } else if (ep.act == 2) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
-            }
-            if (ep.aux_in != nullptr) {
-              const float2 a0 = unpack_bf16x2(aux[g].x), a1 = unpack_bf16x2(aux[g].y), a2 = unpack_bf16x2(aux[g].z),
-                           a3 = unpack_bf16x2(aux[g].w);
-              v[0] *= gelu_erf_grad(a0.x); v[1] *= gelu_erf_grad(a0.y);
-              v[2] *= gelu_erf_grad(a1.x); v[3] *= gelu_erf_grad(a1.y);
-              v[4] *= gelu_erf_grad(a2.x); v[5] *= gelu_erf_grad(a2.y);
-              v[6] *= gelu_erf_grad(a3.x); v[7] *= gelu_erf_grad(a3.y);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= scale;
-            if (ep.residual != nullptr && ep.res_fp32) {
-              const float* pr = reinterpret_cast<const float*>(ep.residual) + lrow * ep.ld_res + col;
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(pr)), r1 = __ldg(reinterpret_cast<const float4*>(pr + 4));
-              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-              v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-            } else if (ep.residual != nullptr) {
-              const float2 a0 = unpack_bf16x2(res[g].x), a1 = unpack_bf16x2(res[g].y), a2 = unpack_bf16x2(res[g].z),
-                           a3 = unpack_bf16x2(res[g].w);
-              v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
-              v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
-            }
-            if (ep.out_fp32) {
-              float* o = reinterpret_cast<float*>(ep.out) + lrow * ep.ld_out + col;
-              float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
-              if (ep.accumulate) { o0 = old[2 * g]; o1 = old[2 * g + 1]; }
-              o0.x += v[0]; o0.y += v[1]; o0.z += v[2]; o0.w += v[3];
-              o1.x += v[4]; o1.y += v[5]; o1.z += v[6]; o1.w += v[7];
-              *reinterpret_cast<float4*>(o) = o0;
-              *reinterpret_cast<float4*>(o + 4) = o1;
-            } else {
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + lrow * ep.ld_out + col) = o;
-            }
-          }
-        }
-      }
+      epilogue_tile<BN>(ep, scale, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, m0, n0, M, N, q, half,
+                        lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -354,6 +361,188 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   return OTB_OK;
 }
 
+
+// ================================================================================================
+// cta_group::2 variant: a CTA pair (two SMs) computes one 256 x 256 output tile with a single tcgen05.mma stream
+// issued by the leader.  Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 columns), so a
+// k-block costs 32 KB of smem traffic per SM instead of 48 KB — the 128 x 256 single-CTA kernel saturates the SM's
+// shared-memory bandwidth (TMA writes + tensor-core reads = 192 B/clk > 128 B/clk) at ~66 % tensor-pipe activity —
+// and the ring deepens to 6 stages.  Barrier protocol: TMA of both CTAs completes on the leader's `full`;
+// tcgen05.commit multicasts `empty` / `tmem_full` to both CTAs; both epilogues arrive on the leader's `tmem_empty`.
+// ================================================================================================
+constexpr int k2Stages = 6;
+constexpr int k2StageBytes = 2 * 128 * kBK * 2;   // A 16 KB + B-half 16 KB
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
+                  int K, GemmEpi ep) {
+  constexpr int BN = 256;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+  uint64_t* full_bar = bars;                    // [k2Stages]  (leader's copy is the live one)
+  uint64_t* empty_bar = bars + k2Stages;        // [k2Stages]  (both CTAs)
+  uint64_t* tfull_bar = bars + 2 * k2Stages;    // [2]         (both CTAs)
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]         (leader's copy is the live one)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int tiles_mp = (M + 255) / 256;          // 256-row pair tiles
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_pt = tiles_mp * tiles_n;
+  const int num_kb = (K + kBK - 1) / kBK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < k2Stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 16); }   // 8 warps x 2 CTAs
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc_2cta(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 10 && lane == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pt = cluster_id; pt < num_pt; pt += num_clusters) {
+      const int m0 = (pt % tiles_mp) * 256 + static_cast<int>(rank) * 128;
+      const int n0 = (pt / tiles_mp) * BN + static_cast<int>(rank) * 128;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * k2StageBytes;
+        uint8_t* sb = sa + 128 * kBK * 2;
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * k2StageBytes);   // bytes of BOTH CTAs
+        const int k0 = kb * kBK;
+        if constexpr (!A_MN) {
+          tma_load_2d_2cta(sa, &map_a, &full_bar[stage], k0, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) tma_load_2d_2cta(sa + c * (kBK * 128), &map_a, &full_bar[stage], m0 + c * 64, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d_2cta(sb, &map_b, &full_bar[stage], k0, n0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) tma_load_2d_2cta(sb + c * (kBK * 128), &map_b, &full_bar[stage], n0 + c * 64, k0);
+        }
+        if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 11 && lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA, single thread) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
+    constexpr uint32_t a_lbo = A_MN ? kBK * 128 : 16, a_kstep = A_MN ? 2048 : 32;
+    constexpr uint32_t b_lbo = B_MN ? kBK * 128 : 16, b_kstep = B_MN ? 2048 : 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int pt = cluster_id; pt < num_pt; pt += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * k2StageBytes);
+        const uint32_t sb = sa + 128 * kBK * 2;
+        const uint64_t da = make_smem_desc(sa, a_lbo, 1024);
+        const uint64_t db = make_smem_desc(sb, b_lbo, 1024);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          umma_bf16_2cta(d_tmem, da + ((k * a_kstep) >> 4), db + ((k * b_kstep) >> 4), idesc, (kb | k) != 0);
+        umma_commit_2cta_mcast(&empty_bar[stage], 0x3);
+        if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_2cta_mcast(&tfull_bar[acc], 0x3);
+    }
+  } else if (warp < 8) {
+    // ===================== epilogue warps (both CTAs; each CTA owns its 128 rows) =====================
+    const int q = warp & 3, half = warp >> 2;
+    float scale = ep.alpha;
+    if (ep.scale_ptr != nullptr) {
+      const float s = __ldg(ep.scale_ptr);
+      scale *= ep.scale_tanh ? tanhf(s) : s;
+    }
+    int it = 0;
+    for (int pt = cluster_id; pt < num_pt; pt += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (pt % tiles_mp) * 256 + static_cast<int>(rank) * 128;
+      const int n0 = (pt / tiles_mp) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN>(ep, scale, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, m0, n0, M, N, q, half,
+                        lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);      // leader's barrier
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm2(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                        const GemmEpi& ep, cudaStream_t stream) {
+  CUtensorMap ma, mb;
+  int rc;
+  if (!A_MN) rc = make_tmap_bf16_2d(&ma, A, M, K, lda, 128, 64);
+  else       rc = make_tmap_bf16_2d(&ma, A, K, M, lda, kBK, 64);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap_bf16_2d(&mb, B, N, K, ldb, 128, 64);
+  else       rc = make_tmap_bf16_2d(&mb, B, K, N, ldb, kBK, 64);
+  if (rc) return rc;
+  auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+    attr_set = true;
+  }
+  const int num_pt = ((M + 255) / 256) * ((N + 255) / 256);
+  const int max_clusters = sm_count() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
+  if (pdl_enabled()) {
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
+  attr[nattr].id = cudaLaunchAttributeClusterDimension;
+  attr[nattr].val.clusterDim.x = 2; attr[nattr].val.clusterDim.y = 1; attr[nattr].val.clusterDim.z = 1;
+  ++nattr;
+  cfg.gridDim = dim3(2 * (num_pt < max_clusters ? num_pt : max_clusters));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = k2SmemBytes;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  OTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, ep));
+  count_launch();
+  return OTB_OK;
+}
+
 }  // namespace otb
 
 extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major, int64_t ldb,
@@ -397,6 +586,16 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   static const bool mc_off = (getenv("OTB_GEMM_NO_MCAST") != nullptr);
   const bool mc = !mc_off && tiles_m >= 2 && (tiles_m % 2 == 0 || tiles_m >= 9) && tiles >= sm_count();
   const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+  // cta_group::2 pair kernel for the large problems (>= one 256x256 pair tile per SM pair)
+  static const int two_cta = [] { const char* e = getenv("OTB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  if (two_cta && !bn128 && ((M + 255) / 256) * ((N + 255) / 256) >= sm_count() / 2) {
+    switch (sel) {
+      case 0: return launch_gemm2<false, false>(A, lda, B, ldb, M, N, K, ep, st);
+      case 1: return launch_gemm2<false, true>(A, lda, B, ldb, M, N, K, ep, st);
+      case 3: return launch_gemm2<true, true>(A, lda, B, ldb, M, N, K, ep, st);
+      default: break;
+    }
+  }
 #define OTB_GEMM_CASE(BN_, A_, B_)                                                                   \
   return mc ? launch_gemm<BN_, A_, B_, true>(A, lda, B, ldb, M, N, K, ep, st)                         \
             : launch_gemm<BN_, A_, B_, false>(A, lda, B, ldb, M, N, K, ep, st)
