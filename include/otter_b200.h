@@ -198,6 +198,22 @@ int otb_media_from_clip(const void* hidden, const float* frame_embs, int F, void
 int otb_fuyu_scatter(const void* word, const void* cont, const int64_t* idx, const int64_t* b_off, void* out,
                      int B, int S, int D, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SURVEY.md §8f row 2 — the steps immediately either side of the hot path in the training step.
+ * Label masking (integer, bit-exact): pipeline/train/instruction_following.py:163-190.
+ *   labels = where(ids == eos, eos, mask_val); for every <answer> the span up to and including its matching
+ *   <|endofchunk|> copies the ids (both pairing passes of the reference); labels[:, 0] = mask_val.
+ * Shifted cross-entropy: src/otter_ai/models/mpt/modeling_mpt.py:430-436 (HF LLaMA computes the same shift):
+ *   target[b,t] = labels[b,t+1], last position and -100 ignored; loss = mean over supervised targets;
+ *   dlogits (optional, same dtype as logits) = d loss / d logits.  ws: fp32 [1 + B*L].
+ * ------------------------------------------------------------------------------------------- */
+int otb_label_mask(const int64_t* input_ids, int B, int L, int64_t eos_id, int64_t answer_id, int64_t eoc_id,
+                   int64_t mask_val, int64_t* labels, void* stream);
+int otb_shifted_cross_entropy(const void* logits, int logits_fp32, int64_t ld, const int64_t* labels, int B, int L,
+                              int V, float* loss, void* dlogits, int64_t ldd, float* ws, void* stream);
+/* x *= *scalar (device scalar; bf16 or fp32 x) — applies the upstream loss gradient without a host sync. */
+int otb_scale_by_scalar(void* x, int x_fp32, int64_t n, const float* scalar, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

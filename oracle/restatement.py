@@ -263,3 +263,34 @@ def m1_forward(vision_x, hidden, media_locations, clip_p, perc_p, gated_ps, q=No
     for gp in gated_ps:
         x = gated_cross_attention_block(x, media, media_locations, gp, q=q)
     return x, media
+
+
+# --------------------------------------------------------------------------------------------
+# label masking (pipeline/train/instruction_following.py:163-190) and the shifted LM loss
+# (src/otter_ai/models/mpt/modeling_mpt.py:430-436)
+# --------------------------------------------------------------------------------------------
+def label_mask_np(input_ids, eos_token_id, answer_token_id, endofchunk_token_id, masking_number=-100):
+    """numpy restatement of `masking()` — integer, bit-exact contract."""
+    ids = np.asarray(input_ids).astype(np.int64)
+    labels = np.where(ids == eos_token_id, eos_token_id, masking_number).astype(np.int64)   # :166
+    for i in range(ids.shape[0]):
+        A = np.nonzero(ids[i] == answer_token_id)[0]                                         # :167
+        E = np.nonzero(ids[i] == endofchunk_token_id)[0]                                     # :168
+        j = 0
+        for a in A:                                                                          # :171-183
+            while j < len(E) and E[j] < a:
+                j += 1
+            if j < len(E):
+                labels[i, a + 1:E[j] + 1] = ids[i, a + 1:E[j] + 1]
+                j += 1
+        for a, e in zip(A, E):                                                               # :185-186
+            labels[i, a + 1:e + 1] = ids[i, a + 1:e + 1]
+    labels[:, 0] = masking_number                                                            # :188
+    return labels
+
+
+def shifted_cross_entropy(logits, labels):
+    """F.cross_entropy(logits.view(-1, V), roll(labels, -1) with last column -100) — modeling_mpt.py:430-436."""
+    _labels = torch.roll(labels, shifts=-1)
+    _labels[:, -1] = -100
+    return F.cross_entropy(logits.reshape(-1, logits.size(-1)).float(), _labels.reshape(-1))

@@ -77,6 +77,9 @@ SIGNATURES = {
     "otb_add_rowbias_f32": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP]),
     "otb_attn_fwd_f32": (_I, [C.POINTER(AttnDesc), _VP]),
     "otb_epilogue_f32": (_I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _I, _I, _VP]),
+    "otb_label_mask": (_I, [_VP, _I, _I, _I64, _I64, _I64, _I64, _VP, _VP]),
+    "otb_shifted_cross_entropy": (_I, [_VP, _I, _I64, _VP, _I, _I, _I, _VP, _VP, _I64, _VP, _VP]),
+    "otb_scale_by_scalar": (_I, [_VP, _I, _I64, _VP, _VP]),
     "otb_im2col_patches": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _I, _VP]),
     "otb_clip_assemble": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "otb_media_from_clip": (_I, [_VP, _VP, _I, _VP, _I, _I, _I, _VP]),

@@ -236,3 +236,36 @@ def test_small_passes():
     ref = fuyu_gather_continuous_embeddings(word.cpu().float(), [c.cpu().float() for c in cont], idx)
     got = F.fuyu_scatter(word, torch.cat(cont), idx.to(dev()), torch.tensor([0, 3], device=dev()))
     assert torch.equal(got.cpu().float(), ref)
+
+
+def test_label_mask_bit_exact_and_shifted_cross_entropy():
+    """device label masking == the reference's masking() (golden, bit-exact) and the fused
+    shifted cross-entropy (+ gradient) == F.cross_entropy on rolled labels (modeling_mpt.py:430-436)."""
+    import os
+    from oracle import restatement as R
+    from otter_b200 import losses
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "label_mask.pt"), weights_only=False)
+    for name, c in g["cases"].items():
+        got = losses.label_mask(c["input_ids"].to(dev()), g["eos"], g["answer"], g["eoc"])
+        assert got.dtype == torch.int64 and torch.equal(got.cpu(), c["labels"]), name
+    torch.manual_seed(0)
+    for dtype, V, tol in ((torch.float32, 1000, 1e-5), (torch.bfloat16, 50432, 2e-3)):
+        B, L = 3, 37
+        logits = (torch.randn(B, L, V) * 2).to(dtype)
+        labels = torch.randint(0, V, (B, L))
+        labels[labels % 5 == 0] = -100
+        labels[1, :] = -100                                   # a fully ignored sequence
+        ref_in = logits.float().clone().requires_grad_(True)
+        ref = R.shifted_cross_entropy(ref_in, labels.clone())
+        (ref * 0.5).backward()
+        x = logits.detach().to(dev()).requires_grad_(True)
+        loss = losses.shifted_cross_entropy(x, labels.to(dev()))
+        (loss * 0.5).backward()
+        assert abs(loss.item() - ref.item()) <= tol * abs(ref.item()) + 1e-6, (dtype, loss.item(), ref.item())
+        gerr = (x.grad.float().cpu() - ref_in.grad).abs().max().item()
+        assert gerr <= (1e-7 if dtype == torch.float32 else 2e-4), (dtype, gerr)
+    # nothing supervised: finite (0) loss, zero gradient
+    x = torch.randn(1, 4, 64, device=dev(), requires_grad=True)
+    loss = losses.shifted_cross_entropy(x, torch.full((1, 4), -100, device=dev()))
+    loss.backward()
+    assert loss.item() == 0.0 and x.grad.abs().max().item() == 0.0
