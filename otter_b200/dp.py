@@ -26,8 +26,10 @@ class FlatGradBuffer:
         self.flat = torch.zeros(off, device=device, dtype=dtype)
         for p, o in zip(self.params, self.offsets):
             view = self.flat[o:o + p.numel()].view(p.shape)
-            p.grad = view if p.dtype == dtype else None
-            if p.dtype in (torch.float32, torch.bfloat16) and dtype == torch.float32:
+            if p.dtype != dtype:
+                raise TypeError(f"FlatGradBuffer({dtype}) needs {dtype} parameters (fp32 master weights); got {p.dtype}")
+            p.grad = view
+            if dtype == torch.float32:
                 p._otb_grad = view          # sink used by otter_b200 backward kernels
                 p._otb_grad_live = False
 

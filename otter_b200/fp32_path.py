@@ -50,7 +50,13 @@ def w6_of(p, pad_to=None):
     if pad_to is not None and w.shape[1] < pad_to:
         w = torch.nn.functional.pad(w, (0, pad_to - w.shape[1]))
     out = F.split3_concat(w.contiguous(), 1)
-    _w6[key] = (weakref.ref(p), p._version, p.data_ptr(), out)
+
+    def _drop(r, key=key):
+        hit = _w6.get(key)
+        if hit is not None and hit[0] is r:
+            del _w6[key]
+
+    _w6[key] = (weakref.ref(p, _drop), p._version, p.data_ptr(), out)
     return out
 
 

@@ -22,6 +22,18 @@ _shadow = {}
 _f32 = {}
 
 
+def _ref(cache, p):
+    """weakref whose callback drops the cache entry (and its device buffer) when the parameter dies."""
+    key = id(p)
+
+    def _drop(r, cache=cache, key=key):
+        hit = cache.get(key)
+        if hit is not None and hit[3] is r:
+            del cache[key]
+
+    return weakref.ref(p, _drop)
+
+
 def _lookup(cache, p, ver, ptr):
     hit = cache.get(id(p))
     if hit is not None and hit[3]() is not p:
@@ -43,7 +55,7 @@ def bf16_of(p):
         return val
     out = hit[2] if (hit is not None and hit[2].shape == t.shape and hit[2].device == t.device) else None
     out = F.cast_bf16(t.float() if t.dtype != torch.float32 else t, out)
-    _shadow[id(p)] = (ver, ptr, out, weakref.ref(p))
+    _shadow[id(p)] = (ver, ptr, out, _ref(_shadow, p))
     return out
 
 
@@ -57,7 +69,7 @@ def f32_of(p):
     if val is not None:
         return val
     out = t.float().contiguous()
-    _f32[id(p)] = (ver, ptr, out, weakref.ref(p))
+    _f32[id(p)] = (ver, ptr, out, _ref(_f32, p))
     return out
 
 
