@@ -361,12 +361,13 @@ def run_cuda(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor",
-                     "kernel": "otb::gemm_bf16_kernel<256,*,*> — the six 4096<->16384 FFN GEMM classes (fwd, dgrad, "
-                               "wgrad) of the gated blocks, 48 launches/step",
+                     "kernel": "otb::gemm2_bf16_kernel (tcgen05 cta_group::2 / TMA) — the six 4096<->16384 FFN GEMM classes "
+                               "(fwd, dgrad, wgrad) of the gated blocks, 48 launches/step",
                      "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": round(ach / peak_tf, 4) if peak_tf else None,
-                     "traffic": 252.5e6, "traffic_note": "dram read+write of one 2048x16384x4096 launch, ncu --set full, "
-                                                         "profiles/r01_ncu_gemm_full.md (algorithmic 285 MB)",
+                     "traffic": 269.4e6, "traffic_note": "dram read+write of one 2048x16384x4096 GELU+aux launch of "
+                                                         "gemm2_bf16_kernel, ncu --set full, profiles/r01_ncu_full_v2.md "
+                                                         "(algorithmic 285 MB)",
                      "peak_source": peak_src, "frac_of_sustained_peak": round(ach / peak_sus, 4),
                      "per_class_us": dom["per_class_us"], "flops_per_launch_avg": dom["flops_avg"],
                      "share_of_step": round(8 * dom["sum_ms"] / step_ms, 3),

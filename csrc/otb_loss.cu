@@ -9,36 +9,49 @@
 
 namespace otb {
 
-__global__ void label_mask_kernel(const long long* __restrict__ ids, int B, int L, long long eos_id,
-                                  long long answer_id, long long eoc_id, long long mask_val,
-                                  long long* __restrict__ labels) {
+// One CTA per sequence: the row is staged in shared memory (coalesced), one thread runs the two sequential
+// pairing passes of the reference on it, and the labels go back out coalesced.
+__global__ void __launch_bounds__(128)
+label_mask_kernel(const long long* __restrict__ ids, int B, int L, long long eos_id, long long answer_id,
+                  long long eoc_id, long long mask_val, long long* __restrict__ labels) {
   pdl_launch_dependents();
   pdl_wait();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const long long* x = ids + static_cast<long long>(b) * L;
-  long long* y = labels + static_cast<long long>(b) * L;
-  for (int i = 0; i < L; ++i) y[i] = (x[i] == eos_id) ? eos_id : mask_val;                   // :166
-  // pass 1 (:170-183): each <answer> pairs with the first not-yet-consumed <|endofchunk|> at or after it
-  int e = 0;                                   // scan position of the endofchunk pointer ("j" walks E in order)
-  for (int a = 0; a < L; ++a) {
-    if (x[a] != answer_id) continue;
-    while (e < L && !(x[e] == eoc_id && e >= a)) ++e;        // while E[j] < a: j += 1  (skips consumed ones too)
-    if (e < L) {
-      for (int p = a + 1; p <= e; ++p) y[p] = x[p];          // labels[a+1 : e+1] = ids[a+1 : e+1]
-      ++e;                                                   // j += 1
+  extern __shared__ long long lm_smem[];
+  long long* x = lm_smem;        // [L]
+  long long* y = lm_smem + L;    // [L]
+  const int b = blockIdx.x;
+  const long long* gx = ids + static_cast<long long>(b) * L;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const long long v = gx[i];
+    x[i] = v;
+    y[i] = (v == eos_id) ? eos_id : mask_val;                                                 // :166
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // pass 1 (:170-183): each <answer> pairs with the first not-yet-consumed <|endofchunk|> after it
+    int e = 0;
+    for (int a = 0; a < L; ++a) {
+      if (x[a] != answer_id) continue;
+      while (e < L && !(x[e] == eoc_id && e >= a)) ++e;      // while E[j] < a: j += 1
+      if (e < L) {
+        for (int p = a + 1; p <= e; ++p) y[p] = x[p];        // labels[a+1 : e+1] = ids[a+1 : e+1]
+        ++e;                                                 // j += 1
+      }
     }
+    // pass 2 (:185-186): zip(answers, endofchunks) — k-th <answer> with k-th <|endofchunk|>
+    int pa = 0, pe = 0;
+    while (true) {
+      while (pa < L && x[pa] != answer_id) ++pa;
+      while (pe < L && x[pe] != eoc_id) ++pe;
+      if (pa >= L || pe >= L) break;
+      for (int p = pa + 1; p <= pe; ++p) y[p] = x[p];
+      ++pa; ++pe;
+    }
+    y[0] = mask_val;                                                                          // :188
   }
-  // pass 2 (:185-186): zip(answers, endofchunks) — k-th <answer> with k-th <|endofchunk|>
-  int pa = 0, pe = 0;
-  while (true) {
-    while (pa < L && x[pa] != answer_id) ++pa;
-    while (pe < L && x[pe] != eoc_id) ++pe;
-    if (pa >= L || pe >= L) break;
-    for (int p = pa + 1; p <= pe; ++p) y[p] = x[p];
-    ++pa; ++pe;
-  }
-  y[0] = mask_val;                                                                            // :188
+  __syncthreads();
+  long long* gy = labels + static_cast<long long>(b) * L;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) gy[i] = y[i];
 }
 
 __device__ __forceinline__ float ld_logit(const float* p, long long i) { return p[i]; }
@@ -69,52 +82,85 @@ __global__ void ce_count_kernel(const long long* __restrict__ labels, long long 
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+// One CTA per (b, t) row.  When the row fits in shared memory (V * sizeof(T) <= 200 KB: 100 KB for MPT's 50 432
+// bf16 logits) it is read from HBM exactly once with 16-byte loads, reduced from smem, and the gradient is written
+// once: 1 read + 1 write = the algorithmic minimum.  Larger rows fall back to re-reading global memory.
+template <typename T, bool kSmem>
+__global__ void __launch_bounds__(512)
 ce_row_kernel(const T* __restrict__ logits, long long ld, const long long* __restrict__ labels, int L, int V,
               const float* __restrict__ count, float* __restrict__ row_loss, T* __restrict__ dlogits, long long ldd) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float sm[8], ss[8];
+  extern __shared__ __align__(16) uint8_t ce_smem[];
+  __shared__ float red[16];
   const long long row = blockIdx.x;
   const long long tgt = shifted_target(labels, L, row);
   const T* x = logits + row * ld;
   T* dx = dlogits ? dlogits + row * ldd : nullptr;
-  if (tgt == -100) {                              // ignored position: zero loss, zero gradient
+  constexpr int VEC = 16 / sizeof(T);
+  const int nvec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (dx == nullptr || (reinterpret_cast<uintptr_t>(dx) & 15) == 0))
+                       ? V / VEC : 0;                          // vector body; the scalar tail covers the rest
+  if (tgt == -100) {                                           // ignored position: zero loss, zero gradient
     if (threadIdx.x == 0) row_loss[row] = 0.f;
-    if (dx) for (int v = threadIdx.x; v < V; v += blockDim.x) st_logit(dx, v, 0.f);
+    if (dx) {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int v = threadIdx.x; v < nvec; v += blockDim.x) reinterpret_cast<uint4*>(dx)[v] = z;
+      for (int v = nvec * VEC + threadIdx.x; v < V; v += blockDim.x) st_logit(dx, v, 0.f);
+    }
     return;
   }
-  // sweep 1: online max / sum-exp
-  float m = -INFINITY, s = 0.f;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
-    const float z = ld_logit(x, v);
-    if (z > m) { s = s * __expf(m - z) + 1.f; m = z; } else { s += __expf(z - m); }
-  }
+  T* sx = reinterpret_cast<T*>(ce_smem);
+  const T* src = x;
+  float m = -INFINITY;
+  if constexpr (kSmem) {
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + v);
+      reinterpret_cast<uint4*>(sx)[v] = u;
+      const T* e = reinterpret_cast<const T*>(&u);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
-    const float mm = fmaxf(m, m2);
-    s = s * __expf(m - mm) + s2 * __expf(m2 - mm);
-    m = mm;
+      for (int i = 0; i < VEC; ++i) m = fmaxf(m, ld_logit(e, i));
+    }
+    for (int v = nvec * VEC + threadIdx.x; v < V; v += blockDim.x) {
+      const T t = x[v];
+      sx[v] = t;
+      m = fmaxf(m, ld_logit(&t, 0));
+    }
+    src = sx;
+  } else {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, ld_logit(x, v));
   }
-  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; ss[threadIdx.x >> 5] = s; }
+  // block max
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
-  float M = sm[0], S = ss[0];
+  float M = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) M = fmaxf(M, red[i]);
+  __syncthreads();
+  // block sum of exp(x - M)
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) s += __expf(ld_logit(src, v) - M);
 #pragma unroll
-  for (int i = 1; i < 8; ++i) {
-    const float mm = fmaxf(M, sm[i]);
-    S = S * __expf(M - mm) + ss[i] * __expf(sm[i] - mm);
-    M = mm;
-  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float S = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) S += red[i];
   const float lse = M + logf(S);
-  if (threadIdx.x == 0) row_loss[row] = lse - ld_logit(x, tgt);
+  if (threadIdx.x == 0) row_loss[row] = lse - ld_logit(src, tgt);
   if (dx) {
     const float inv = 1.0f / fmaxf(*count, 1.0f);
-    for (int v = threadIdx.x; v < V; v += blockDim.x) {
-      const float p = __expf(ld_logit(x, v) - lse);
-      st_logit(dx, v, (p - ((v == tgt) ? 1.f : 0.f)) * inv);
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      __align__(16) T o[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int c = v * VEC + i;
+        st_logit(o, i, (__expf(ld_logit(src, c) - lse) - ((c == tgt) ? 1.f : 0.f)) * inv);
+      }
+      reinterpret_cast<uint4*>(dx)[v] = *reinterpret_cast<const uint4*>(o);
     }
+    for (int v = nvec * VEC + threadIdx.x; v < V; v += blockDim.x)
+      st_logit(dx, v, (__expf(ld_logit(src, v) - lse) - ((v == tgt) ? 1.f : 0.f)) * inv);
   }
 }
 
@@ -154,7 +200,14 @@ using namespace otb;
 extern "C" int otb_label_mask(const int64_t* input_ids, int B, int L, int64_t eos_id, int64_t answer_id, int64_t eoc_id,
                               int64_t mask_val, int64_t* labels, void* stream) {
   OTB_CHECK_ARG(input_ids && labels && B > 0 && L > 0, "otb_label_mask: bad argument");
-  OTB_CHECK_CUDA(launch_k(label_mask_kernel, dim3((B + 31) / 32), dim3(32), 0, ST(stream),
+  const size_t lm_smem = static_cast<size_t>(L) * 16;
+  OTB_CHECK_ARG(lm_smem <= 200 * 1024, "otb_label_mask: L too long for the shared-memory staging (max 12800)");
+  static bool lm_attr = false;
+  if (!lm_attr) {
+    OTB_CHECK_CUDA(cudaFuncSetAttribute(label_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    lm_attr = true;
+  }
+  OTB_CHECK_CUDA(launch_k(label_mask_kernel, dim3(B), dim3(128), lm_smem, ST(stream),
                           reinterpret_cast<const long long*>(input_ids), B, L, (long long)eos_id, (long long)answer_id,
                           (long long)eoc_id, (long long)mask_val, reinterpret_cast<long long*>(labels)));
   count_launch();
@@ -171,14 +224,22 @@ extern "C" int otb_shifted_cross_entropy(const void* logits, int logits_fp32, in
   float* row_loss = ws + 1;
   const long long* lab = reinterpret_cast<const long long*>(labels);
   OTB_CHECK_CUDA(launch_k(ce_count_kernel, dim3(1), dim3(1024), 0, ST(stream), lab, rows, L, count));
-  if (logits_fp32)
-    OTB_CHECK_CUDA(launch_k(ce_row_kernel<float>, dim3((unsigned)rows), dim3(256), 0, ST(stream),
-                            static_cast<const float*>(logits), (long long)ld, lab, L, V, (const float*)count, row_loss,
-                            static_cast<float*>(dlogits), (long long)ldd));
-  else
-    OTB_CHECK_CUDA(launch_k(ce_row_kernel<bf16>, dim3((unsigned)rows), dim3(256), 0, ST(stream),
-                            static_cast<const bf16*>(logits), (long long)ld, lab, L, V, (const float*)count, row_loss,
-                            static_cast<bf16*>(dlogits), (long long)ldd));
+  const size_t row_bytes = static_cast<size_t>(V) * (logits_fp32 ? 4 : 2);
+  const bool in_smem = row_bytes <= 200 * 1024;
+  const size_t ce_smem = in_smem ? ((row_bytes + 15) & ~size_t(15)) : 0;
+  static bool ce_attr = false;
+  if (!ce_attr) {
+    OTB_CHECK_CUDA(cudaFuncSetAttribute(ce_row_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
+    OTB_CHECK_CUDA(cudaFuncSetAttribute(ce_row_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
+    ce_attr = true;
+  }
+#define OTB_CE_LAUNCH(T_, S_)                                                                                       \
+  OTB_CHECK_CUDA(launch_k(ce_row_kernel<T_, S_>, dim3((unsigned)rows), dim3(512), ce_smem, ST(stream),              \
+                          static_cast<const T_*>(logits), (long long)ld, lab, L, V, (const float*)count, row_loss,  \
+                          static_cast<T_*>(dlogits), (long long)ldd))
+  if (logits_fp32) { if (in_smem) OTB_CE_LAUNCH(float, true); else OTB_CE_LAUNCH(float, false); }
+  else             { if (in_smem) OTB_CE_LAUNCH(bf16, true);  else OTB_CE_LAUNCH(bf16, false); }
+#undef OTB_CE_LAUNCH
   OTB_CHECK_CUDA(launch_k(ce_finalize_kernel, dim3(1), dim3(256), 0, ST(stream), (const float*)row_loss, rows,
                           (const float*)count, loss));
   count_launch(3);
