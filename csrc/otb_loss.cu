@@ -93,6 +93,7 @@ ce_row_kernel(const T* __restrict__ logits, long long ld, const long long* __res
   pdl_wait();
   extern __shared__ __align__(16) uint8_t ce_smem[];
   __shared__ float red[16];
+  __shared__ float tgt_logit;
   const long long row = blockIdx.x;
   const long long tgt = shifted_target(labels, L, row);
   const T* x = logits + row * ld;
@@ -137,9 +138,18 @@ ce_row_kernel(const T* __restrict__ logits, long long ld, const long long* __res
   float M = red[0];
   for (int i = 1; i < (blockDim.x >> 5); ++i) M = fmaxf(M, red[i]);
   __syncthreads();
-  // block sum of exp(x - M)
+  // block sum of exp(x - M); with the row in smem the exponentials are kept in place (as T) for the gradient
   float s = 0.f;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) s += __expf(ld_logit(src, v) - M);
+  if constexpr (kSmem) {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float e = __expf(ld_logit(sx, v) - M);
+      s += e;
+      if (v == tgt) tgt_logit = ld_logit(sx, v);    // the target logit, needed for the loss
+      st_logit(sx, v, e);
+    }
+  } else {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) s += __expf(ld_logit(src, v) - M);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -147,20 +157,22 @@ ce_row_kernel(const T* __restrict__ logits, long long ld, const long long* __res
   float S = 0.f;
   for (int i = 0; i < (blockDim.x >> 5); ++i) S += red[i];
   const float lse = M + logf(S);
-  if (threadIdx.x == 0) row_loss[row] = lse - ld_logit(src, tgt);
+  if (threadIdx.x == 0) row_loss[row] = lse - (kSmem ? tgt_logit : ld_logit(src, tgt));
   if (dx) {
     const float inv = 1.0f / fmaxf(*count, 1.0f);
+    const float invS = 1.0f / S;
+    auto prob = [&](int c) { return kSmem ? ld_logit(sx, c) * invS : __expf(ld_logit(src, c) - lse); };
     for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
       __align__(16) T o[VEC];
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const int c = v * VEC + i;
-        st_logit(o, i, (__expf(ld_logit(src, c) - lse) - ((c == tgt) ? 1.f : 0.f)) * inv);
+        st_logit(o, i, (prob(c) - ((c == tgt) ? 1.f : 0.f)) * inv);
       }
       reinterpret_cast<uint4*>(dx)[v] = *reinterpret_cast<const uint4*>(o);
     }
     for (int v = nvec * VEC + threadIdx.x; v < V; v += blockDim.x)
-      st_logit(dx, v, (__expf(ld_logit(src, v) - lse) - ((v == tgt) ? 1.f : 0.f)) * inv);
+      st_logit(dx, v, (prob(v) - ((v == tgt) ? 1.f : 0.f)) * inv);
   }
 }
 

@@ -62,11 +62,15 @@ class PerceiverBlockFn(torch.autograd.Function):
         D = x.shape[1]
         n1, n2 = x.shape[0] // BT, lat.shape[0] // BT
         inner = heads * 64
-        xn, mx, rx = F.layernorm_fwd(x, f32_of(nm_w), f32_of(nm_b))                         # :159
-        ln, ml, rl = F.layernorm_fwd(lat, f32_of(nl_w), f32_of(nl_b))                       # :161
+        # cat(x, latents) (:166) without a copy: both LayerNorms write into one [media rows | latent rows] buffer,
+        # so to_kv is ONE GEMM and the attention kernel reads the two row blocks as its two key sources
+        R1, R2 = x.shape[0], lat.shape[0]
+        kv_in = torch.empty((R1 + R2, D), device=x.device, dtype=BF16)
+        xn, mx, rx = F.layernorm_fwd(x, f32_of(nm_w), f32_of(nm_b), out=kv_in[:R1])        # :159
+        ln, ml, rl = F.layernorm_fwd(lat, f32_of(nl_w), f32_of(nl_b), out=kv_in[R1:])      # :161
         q = F.linear_fwd(ln, bf16_of(wq))                                                   # :165
-        kv_x = F.linear_fwd(xn, bf16_of(wkv))                                               # :166-167 (no cat:
-        kv_l = F.linear_fwd(ln, bf16_of(wkv))                                               #  two key sources)
+        kv = F.linear_fwd(kv_in, bf16_of(wkv))                                              # :166-167
+        kv_x, kv_l = kv[:R1], kv[R1:]
         spec = F.AttnSpec(q, 0, kv_x, 0, inner, BT, heads, n2, n1, 0.125, kv2=kv_l, k2_col0=0, v2_col0=inner, Sk2=n2)
         o, lse = F.attn_fwd(spec)                                                           # :168-179 fused
         lat1 = F.linear_fwd(o, bf16_of(wo), residual=lat)                                   # :180
@@ -74,16 +78,18 @@ class PerceiverBlockFn(torch.autograd.Function):
         z = torch.empty((lat.shape[0], w1.shape[0]), device=x.device, dtype=BF16)
         hh = F.linear_fwd(h0, bf16_of(w1), act=1, aux_out=z)
         lat2 = F.linear_fwd(hh, bf16_of(w2), residual=lat1)                                 # :184
-        ctx.save_for_backward(x, lat, xn, ln, q, kv_x, kv_l, o, lse, lat1, h0, z, hh, mx, rx, ml, rl, mf, rf)
+        ctx.save_for_backward(x, lat, kv_in, q, kv, o, lse, lat1, h0, z, hh, mx, rx, ml, rl, mf, rf)
         ctx.params = (nm_w, nm_b, nl_w, nl_b, wq, wkv, wo, ff_w, ff_b, w1, w2)
         ctx.cfg = (BT, need_dx, heads, n1, n2, D, inner)
         return lat2
 
     @staticmethod
     def backward(ctx, dlat2):
-        x, lat, xn, ln, q, kv_x, kv_l, o, lse, lat1, h0, z, hh, mx, rx, ml, rl, mf, rf = ctx.saved_tensors
+        x, lat, kv_in, q, kv, o, lse, lat1, h0, z, hh, mx, rx, ml, rl, mf, rf = ctx.saved_tensors
         nm_w, nm_b, nl_w, nl_b, wq, wkv, wo, ff_w, ff_b, w1, w2 = ctx.params
         BT, need_dx, heads, n1, n2, D, inner = ctx.cfg
+        R1 = x.shape[0]
+        xn, ln, kv_x, kv_l = kv_in[:R1], kv_in[R1:], kv[:R1], kv[R1:]
         sink = GradSink()
         ws = _WgradStream(x.device)
         dlat2 = _as_bf16_2d(dlat2, D)
@@ -104,22 +110,21 @@ class PerceiverBlockFn(torch.autograd.Function):
         # fused attention backward
         spec = F.AttnSpec(q, 0, kv_x, 0, inner, BT, heads, n2, n1, 0.125, kv2=kv_l, k2_col0=0, v2_col0=inner, Sk2=n2)
         dq = torch.empty_like(q)
-        dkv_x = torch.empty_like(kv_x)
-        dkv_l = torch.empty_like(kv_l)
+        dkv = torch.empty_like(kv)
+        dkv_x, dkv_l = dkv[:R1], dkv[R1:]
         F.attn_bwd(spec, o, 0, lse, do, 0, dq, 0, dkv_x, 0, inner, dkv_l, 0, inner)
-        # projections
+        # projections: to_kv's wgrad and dgrad are single GEMMs over the [media | latent] rows
         gq, accq = sink.target(wq)
         gkv, acckv = sink.target(wkv)
 
         def _proj_wgrads():
             F.linear_wgrad(dq, ln, out=gq, accumulate=accq)
-            F.linear_wgrad(dkv_x, xn, out=gkv, accumulate=acckv)
-            F.linear_wgrad(dkv_l, ln, out=gkv, accumulate=True)
+            F.linear_wgrad(dkv, kv_in, out=gkv, accumulate=acckv)
 
         ws.run(_proj_wgrads)
-        dln = F.linear_dgrad(dq, bf16_of(wq))
-        dln = F.linear_dgrad(dkv_l, bf16_of(wkv), residual=dln)
-        dxn = F.linear_dgrad(dkv_x, bf16_of(wkv))
+        dkv_in = F.linear_dgrad(dkv, bf16_of(wkv))                              # [d xn | d ln (kv part)]
+        dxn = dkv_in[:R1]
+        dln = F.linear_dgrad(dq, bf16_of(wq), residual=dkv_in[R1:])
         # norms
         gw, acc = sink.target(nl_w)
         gb, _ = sink.target(nl_b)

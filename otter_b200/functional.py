@@ -122,16 +122,17 @@ def linear_wgrad(dy, x, *, out=None, accumulate=False, **epi):
 # ------------------------------------------------------------------------------------------------
 # LayerNorm
 # ------------------------------------------------------------------------------------------------
-def layernorm_fwd(x, gamma, beta, eps=1e-5, want_stats=True):
+def layernorm_fwd(x, gamma, beta, eps=1e-5, want_stats=True, out=None):
     x2 = _mat(x, "x")
     _req(gamma, torch.float32, "gamma"), _req(beta, torch.float32, "beta")
     rows, D = x2.shape
-    y = torch.empty((rows, D), device=x.device, dtype=BF16)
+    y = out if out is not None else torch.empty((rows, D), device=x.device, dtype=BF16)
+    assert y.shape == (rows, D) and y.stride(1) == 1
     mean = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
     check(_lib.load().otb_layernorm_fwd(_p(x2), x2.stride(0), _p(gamma), _p(beta), _p(y), y.stride(0), _p(mean),
                                         _p(rstd), rows, D, eps, _stream()), "otb_layernorm_fwd")
-    return y.view(x.shape), mean, rstd
+    return (y if out is not None else y.view(x.shape)), mean, rstd
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, add=None, want_dx=True, dgamma=None, dbeta=None, accumulate=False,
