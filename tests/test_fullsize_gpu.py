@@ -90,3 +90,63 @@ def test_c5_fuyu_patch_linear_and_scatter():
     err = (out.float().cpu() - ref).abs()
     assert err.max().item() <= 2e-2 + 1e-2 * ref.abs().max().item()
     assert torch.equal(out[0, :5].cpu(), word[0, :5]) and torch.equal(out[0, 5 + n_p:].cpu(), word[0, 5 + n_p:])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ragged / degenerate shapes against the CPU oracle (production bf16 mode and the fp32-grade forward mode)
+# ---------------------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    return ((a.detach().float().cpu() - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("B,L,T,n,locs,attend_previous", [
+    (1, 1, 1, 64, [[]], True),                         # cached decode step: one token, no <image> (reference quirk §3.3)
+    (3, 77, 3, 32, [[0, 30, 60], [5], []], True),      # ragged <image> counts per row, 32 latents per media, odd L
+    (2, 130, 2, 64, [[0, 1], [128, 129]], False),      # adjacent <image> tokens, tile-boundary positions, attend_previous=False
+    (1, 9, 5, 8, [[0, 2, 4, 6, 8]], True),             # 5 media x 8 latents = 40 keys (partial key tile)
+])
+def test_gated_block_ragged_shapes_vs_oracle(B, L, T, n, locs, attend_previous):
+    import otter_b200
+    from otter_b200.modeling_otter import OtterGatedCrossAttentionBlock
+    torch.manual_seed(3)
+    D, Dv = 256, 128
+    gb = OtterGatedCrossAttentionBlock(dim=D, dim_visual=Dv).to(DEV)
+    gb.attn_gate.fill_(0.8), gb.ff_gate.fill_(-0.6)
+    x = torch.randn(B, L, D, device=DEV)
+    media = torch.randn(B, T, n, Dv, device=DEV)
+    loc = torch.zeros(B, L, dtype=torch.bool)
+    for b, ps in enumerate(locs):
+        loc[b, ps] = True
+    p = {k: v.detach().float().cpu() for k, v in gb.state_dict().items()}
+    ref = R.gated_cross_attention_block(x.cpu(), media.cpu(), loc, p, attend_previous=attend_previous)
+    out = gb(x, media, media_locations=loc.to(DEV), attend_previous=attend_previous)
+    assert _rel(out, ref) < 1.5e-2
+    with otter_b200.precision("fp32"):
+        out32 = gb(x, media, media_locations=loc.to(DEV), attend_previous=attend_previous)
+    err = (out32.float().cpu() - ref).abs()
+    assert (err > 1e-5 + 1e-3 * ref.abs()).sum().item() == 0, err.max().item()
+
+
+@pytest.mark.parametrize("b,T,Fr,v,n_lat", [(1, 1, 1, 1, 64), (2, 3, 2, 50, 32), (1, 1, 1, 257, 128)])
+def test_resampler_odd_shapes_vs_oracle(b, T, Fr, v, n_lat):
+    """1 media token, non-multiple-of-64 token counts, 32 / 128 latents, T > 1 with frame embeddings."""
+    import otter_b200
+    from otter_b200.modeling_otter import OtterPerceiverResampler
+    torch.manual_seed(4)
+    rs = OtterPerceiverResampler(dim=128, depth=2, num_latents=n_lat, max_num_frames=4).to(DEV)
+    x = torch.randn(b, T, Fr, v, 128, device=DEV)
+    wgt = torch.randn(b, T, n_lat, 128, device=DEV)
+    out = rs(x)
+    (out.float() * wgt).mean().backward()
+    p = {k: v_.detach().float().cpu().requires_grad_(True) for k, v_ in rs.state_dict().items()}
+    ref = R.perceiver_resampler(x.cpu(), p)
+    (ref * wgt.cpu()).mean().backward()
+    assert _rel(out, ref.detach()) < 1.5e-2
+    for k in ("latents", "frame_embs", "layers.1.to_q.weight", "layers.0.norm_media.bias"):
+        got, want = dict(rs.named_parameters())[k].grad.float().cpu(), p[k].grad
+        assert (got - want).norm() <= 5e-2 * want.norm() + 1e-7, (k, (got - want).norm().item(), want.norm().item())
+    with torch.no_grad(), otter_b200.precision("fp32"):
+        out32 = rs(x)
+    err = (out32.float().cpu() - ref.detach()).abs()
+    assert (err > 1e-5 + 1e-3 * ref.detach().abs()).sum().item() == 0, err.max().item()
