@@ -321,3 +321,69 @@ def test_fp32_mode_tiny_full_model_logits(monkeypatch):
         out = model(vision_x=vision_x, lang_x=lang_x, attention_mask=torch.ones_like(lang_x), labels=labels)
     ns_close(out.logits, g["logits"], "fp32 tiny model logits")
     assert abs(out.loss.item() - g["loss"].item()) <= 1e-3 * abs(g["loss"].item()) + 1e-5
+
+
+def _tiny_model(monkeypatch, g):
+    from transformers import LlamaConfig
+    from otter_b200 import otter_hf
+    monkeypatch.setattr(otter_hf, "AutoTokenizer", FakeTokenizer)
+    tc = LlamaConfig(**{k: v for k, v in g["text_config"].items() if k in (
+        "vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+        "num_key_value_heads", "max_position_embeddings")})
+    td = tc.to_dict()
+    td["_name_or_path"] = "llama-tiny"
+    td["architectures"] = ["LlamaForCausalLM"]
+    cfg = otter_hf.OtterConfig(vision_config={k: v for k, v in g["vision_config"].items() if k in (
+        "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "image_size", "patch_size",
+        "hidden_act")}, text_config=td, cross_attn_every_n_layers=2)
+    cfg.text_config._name_or_path = "llama-tiny"
+    cfg.text_config.architectures = ["LlamaForCausalLM"]
+    model = otter_hf.OtterForConditionalGeneration(cfg)
+    load_seeded_(model, g["seed"], kinds={"perceiver.latents": "randn",
+                                          "vision_encoder.vision_model.embeddings.class_embedding": "emb",
+                                          "vision_encoder.vision_model.embeddings.position_embedding.weight": "emb",
+                                          "lang_encoder.model.embed_tokens.weight": "emb"})
+    return model.to(DEV).eval()
+
+
+def test_generate_matches_reference_greedy(monkeypatch):
+    """generate() (reference :1000-1042; pipeline/demos/demo_models.py:64 call pattern): greedy decoding with the HF
+    KV cache — cached steps see a single token with no <image>, i.e. the zero-attention rows.
+    fp32-grade mode must reproduce the reference's token ids exactly; production mode must run the same path."""
+    import otter_b200
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = gold("tiny_generate.pt")
+    model = _tiny_model(monkeypatch, g)
+    lang_x = g["lang_x"].to(DEV)
+    vision_x = seeded_tensor("in.gen.vision_x", (2, 1, 1, 3, 224, 224), g["seed"], "randn").to(DEV)
+    kw = dict(vision_x=vision_x, lang_x=lang_x, attention_mask=torch.ones_like(lang_x), max_new_tokens=5,
+              do_sample=False, num_beams=1)
+    with otter_b200.precision("fp32"):
+        out32 = model.generate(**kw)
+    assert torch.equal(out32.cpu(), g["generated"]), (out32.cpu(), g["generated"])
+    assert not model.lang_encoder.is_conditioned()
+    out = model.generate(**kw)                                   # production (bf16) numerics: same plumbing
+    assert out.shape == g["generated"].shape and torch.equal(out[:, :9].cpu(), g["lang_x"])
+
+
+def test_backward_is_deterministic():
+    """No atomics anywhere: two identical forward/backward passes give bit-identical outputs and gradients."""
+    from otter_b200.modeling_otter import OtterGatedCrossAttentionBlock, OtterPerceiverResampler
+    torch.manual_seed(0)
+    rs = OtterPerceiverResampler(dim=256, depth=2, max_num_frames=4).to(DEV)
+    gb = OtterGatedCrossAttentionBlock(dim=512, dim_visual=256).to(DEV)
+    with torch.no_grad():
+        gb.attn_gate.fill_(0.5), gb.ff_gate.fill_(0.5)
+    feats = torch.randn(3, 2, 2, 100, 256, device=DEV)
+    x = torch.randn(3, 200, 512, device=DEV)
+    loc = torch.zeros(3, 200, dtype=torch.bool, device=DEV)
+    loc[:, 0] = True
+    loc[:, 90] = True
+    runs = []
+    for _ in range(2):
+        for p in list(rs.parameters()) + list(gb.parameters()):
+            p.grad = None
+        out = gb(x, rs(feats), media_locations=loc)
+        out.float().pow(2).mean().backward()
+        runs.append([out.detach().clone()] + [p.grad.clone() for p in list(rs.parameters()) + list(gb.parameters())])
+    assert all(torch.equal(a, b) for a, b in zip(*runs))
