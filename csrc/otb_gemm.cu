@@ -109,7 +109,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, float scale, ui
         }
         if (ep.act == 1) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+          for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
         } else if (ep.act == 2) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
@@ -117,10 +117,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, float scale, ui
         if (ep.aux_in != nullptr) {
           const float2 a0 = unpack_bf16x2(aux[g].x), a1 = unpack_bf16x2(aux[g].y), a2 = unpack_bf16x2(aux[g].z),
                        a3 = unpack_bf16x2(aux[g].w);
-          v[0] *= gelu_erf_grad(a0.x); v[1] *= gelu_erf_grad(a0.y);
-          v[2] *= gelu_erf_grad(a1.x); v[3] *= gelu_erf_grad(a1.y);
-          v[4] *= gelu_erf_grad(a2.x); v[5] *= gelu_erf_grad(a2.y);
-          v[6] *= gelu_erf_grad(a3.x); v[7] *= gelu_erf_grad(a3.y);
+          v[0] *= gelu_grad_fast(a0.x); v[1] *= gelu_grad_fast(a0.y);
+          v[2] *= gelu_grad_fast(a1.x); v[3] *= gelu_grad_fast(a1.y);
+          v[4] *= gelu_grad_fast(a2.x); v[5] *= gelu_grad_fast(a2.y);
+          v[6] *= gelu_grad_fast(a3.x); v[7] *= gelu_grad_fast(a3.y);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] *= scale;
