@@ -55,3 +55,19 @@ def test_ops_reject_cpu_tensors_loudly():
     from otter_b200 import functional as F
     with pytest.raises(_lib.OtbError, match="CUDA tensor"):
         F.linear_fwd(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_sass_is_blackwell_native():
+    """The built library must contain 5th-gen tensor-core / TMA / TMEM machine code (B200_PROFILING.md:
+    tcgen05.mma -> UTC*MMA, TMA -> UTMALDG, tcgen05.ld -> LDTM) and no legacy mma.sync path (HMMA)."""
+    import shutil
+    import subprocess
+    from otter_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS"):
+        assert mnemonic in sass, f"{mnemonic} missing from the SASS"
+    assert "UTCHMMA.2CTA" in sass or "2CTA" in sass, "cta_group::2 MMA missing"
+    assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync (HMMA) found"
