@@ -482,7 +482,9 @@ def main():
     ap.add_argument("--per-gpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--seq-len", type=int, default=256, help="text length L (SURVEY.md §8d sweeps 128/256/512/1024)")
     args = ap.parse_args()
+    CFG["L"] = args.seq_len
     if args.impl == "reference":
         run_reference(args)
     else:
