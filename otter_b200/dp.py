@@ -29,7 +29,7 @@ class _CommHandle:
 
 
 class FlatGradBuffer:
-    def __init__(self, params, device=None, dtype=torch.float32, comm_dtype=None):
+    def __init__(self, params, device=None, dtype=torch.float32, comm_dtype=None, nccl_registered=False):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -40,12 +40,14 @@ class FlatGradBuffer:
             self.offsets.append(off)
             off += (p.numel() + 3) // 4 * 4
         self.numel = off
-        self.flat = torch.zeros(off, device=device, dtype=dtype)
+        self._pools = []
+        self._registered = bool(nccl_registered)
+        self.flat = self._alloc(off, dtype, device)
         # optional wire format of the collective (SURVEY.md §8e budgets the bf16 payload: 2.36 GB instead of 4.72 GB);
         # gradients are still produced, accumulated and handed to the optimizer in `dtype`
         self.comm = None
         if comm_dtype is not None and comm_dtype != dtype:
-            self.comm = torch.empty(off, device=device, dtype=comm_dtype)
+            self.comm = self._alloc(off, comm_dtype, device)
         for p, o in zip(self.params, self.offsets):
             view = self.flat[o:o + p.numel()].view(p.shape)
             if p.dtype != dtype:
@@ -54,6 +56,22 @@ class FlatGradBuffer:
             if dtype == torch.float32:
                 p._otb_grad = view          # sink used by otter_b200 backward kernels
                 p._otb_grad_live = False
+
+    def _alloc(self, n, dtype, device):
+        """Plain zero-filled allocation, or (nccl_registered=True) one drawn from NCCL's own allocator and registered
+        with the communicator, so the collective can run zero-copy / in-switch (NVLS) on the user buffer instead of
+        staging through NCCL's internal buffers.  Needs an initialised NCCL process group; fails loudly otherwise."""
+        if not self._registered:
+            return torch.zeros(n, device=device, dtype=dtype)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl":
+            raise RuntimeError("nccl_registered=True needs an initialised NCCL process group")
+        backend = dist.distributed_c10d._get_default_group()._get_backend(torch.device(device))
+        pool = torch.cuda.MemPool(backend.mem_allocator)
+        with torch.cuda.use_mem_pool(pool):
+            t = torch.zeros(n, device=device, dtype=dtype)
+        backend.register_mem_pool(pool)
+        self._pools.append(pool)              # keep the pool (and the registration) alive with the buffer
+        return t
 
     def begin_step(self):
         """Start a step.  Parameters whose gradients are written by otter_b200 kernels (`_otb_sink_user`, learned
