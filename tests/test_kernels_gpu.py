@@ -67,7 +67,7 @@ def test_gemm_layouts_and_epilogues():
     assert_close(y2, big[:, 256:512].float() @ w.float().t(), BF_RTOL, BF_ATOL, "strided A")
 
 
-@pytest.mark.parametrize("rows,D", [(37, 256), (512, 1024), (300, 4096)])
+@pytest.mark.parametrize("rows,D", [(37, 256), (512, 1024), (300, 4096), (101, 3072), (2, 2048)])
 def test_layernorm_fwd_bwd(rows, D):
     from otter_b200 import functional as F
     x = rnd(rows, D, scale=2.0)
