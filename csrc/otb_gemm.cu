@@ -737,7 +737,7 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   // OTB_GEMM2_MIN_PAIRS: smallest number of 256x256 pair tiles that goes to the pair kernel (default: one per SM pair)
   static const int min_pairs = [] { const char* v = getenv("OTB_GEMM2_MIN_PAIRS"); return v ? atoi(v) : 0; }();
   const int pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
-  const bool pair_ok = min_pairs > 0 ? (pair_tiles >= min_pairs && N >= 256) : (!bn128 && pair_tiles >= sm_count() / 2);
+  const bool pair_ok = min_pairs > 0 ? (pair_tiles >= min_pairs && N >= 256 && M > 128) : (!bn128 && pair_tiles >= sm_count() / 2);
   if (two_cta && pair_ok) {
 #define OTB_GEMM2_CASE(A_, B_)                                                        \
   return ep.tma_out ? launch_gemm2<A_, B_, true>(A, lda, B, ldb, M, N, K, ep, st)     \
