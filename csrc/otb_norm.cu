@@ -343,6 +343,42 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
     }
   }
 }
+// Multi-tensor cast: one launch re-derives the bf16 copies of a whole list of fp32 tensors.  The device table holds one
+// {src, dst, n, first_block} record per tensor; block b finds its tensor by binary search over first_block and
+// converts elements [(b - first_block) * 4096, +4096) of it.
+struct CastSeg {
+  const float* src;
+  bf16* dst;
+  long long n;
+  long long blk0;
+};
+static_assert(sizeof(CastSeg) == 32, "table layout is part of the C ABI: 4 x int64 per tensor");
+constexpr int kCastSegElems = 4096;
+__global__ void __launch_bounds__(256) cast_multi_kernel(const CastSeg* __restrict__ segs, int nseg) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long b = blockIdx.x;
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&segs[mid].blk0) <= b) lo = mid; else hi = mid - 1;
+  }
+  const float* src = segs[lo].src;
+  bf16* dst = segs[lo].dst;
+  const long long n = segs[lo].n;
+  const long long base = (b - segs[lo].blk0) * kCastSegElems;
+#pragma unroll
+  for (int it = 0; it < kCastSegElems / (256 * 8); ++it) {
+    const long long i = base + (static_cast<long long>(it) * 256 + threadIdx.x) * 8;
+    if (i + 8 <= n) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + i)), c = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+      const float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      *reinterpret_cast<uint4*>(dst + i) = pack8(f);
+    } else {
+      for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16(src[k]);
+    }
+  }
+}
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
   pdl_launch_dependents();
   pdl_wait();
@@ -692,6 +728,16 @@ extern "C" int otb_text_time(const uint8_t* media_locations, int B, int L, int a
                              void* stream) {
   OTB_CHECK_ARG(media_locations && text_time && B > 0 && L > 0, "otb_text_time: bad argument");
   OTB_CHECK_CUDA(launch_k(text_time_kernel, dim3((B + 63) / 64), dim3(64), 0, ST(stream), media_locations, B, L, attend_previous, text_time));
+  count_launch();
+  OTB_CHECK_CUDA(cudaGetLastError());
+  return OTB_OK;
+}
+
+extern "C" int otb_cast_f32_bf16_multi(const void* table, int n_tensors, int64_t total_blocks, void* stream) {
+  OTB_CHECK_ARG(table && n_tensors > 0 && total_blocks > 0 && total_blocks < (1ll << 31),
+                "otb_cast_f32_bf16_multi: bad argument");
+  OTB_CHECK_CUDA(launch_k(cast_multi_kernel, dim3(static_cast<unsigned>(total_blocks)), dim3(256), 0, ST(stream),
+                          static_cast<const CastSeg*>(table), n_tensors));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;

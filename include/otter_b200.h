@@ -149,6 +149,11 @@ int otb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, 
 /* dst(bf16)[i] = src(fp32)[i]  — bf16 shadow of fp32 master weights (autocast-equivalent). */
 int otb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int otb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+/* The same cast for a LIST of tensors in one launch (all trainable weights after an optimizer step).
+ * table: device array of n_tensors records {const float* src; bf16* dst; int64 n; int64 first_block}, 32 bytes each,
+ * sorted by first_block; tensor t owns blocks [first_block_t, first_block_t + ceil(n_t / 4096)); total_blocks is
+ * their sum.  src / dst must be 16-byte aligned. */
+int otb_cast_f32_bf16_multi(const void* table, int n_tensors, int64_t total_blocks, void* stream);
 /* out[r,:] = bf16(src[(r / div) % mod, :])  fp32 [mod][D] -> bf16 [rows][D]; latents repeat (:232). */
 int otb_bcast_rows(const float* src, int div, int mod, void* out, int rows, int D, void* stream);
 /* out[r,:] = x[r,:] + bias[(r / div) % mod, :]   bf16 [rows][D] + fp32 [mod][D]  (frame_embs add, :224-226) */

@@ -246,6 +246,15 @@ def cast_bf16(src, out=None):
     return out
 
 
+CAST_MULTI_BLOCK = 4096      # elements per block of otb_cast_f32_bf16_multi (kCastSegElems)
+
+
+def cast_bf16_multi(table, n_tensors, total_blocks):
+    """table: int64 [n_tensors, 4] on the device = {src ptr, dst ptr, numel, first block} per tensor."""
+    assert table.dtype == torch.int64 and table.is_contiguous() and table.shape == (n_tensors, 4)
+    check(_lib.load().otb_cast_f32_bf16_multi(_p(table), n_tensors, total_blocks, _stream()), "otb_cast_f32_bf16_multi")
+
+
 def cast_f32(src, out=None):
     _req(src, BF16, "src")
     src = src.contiguous()

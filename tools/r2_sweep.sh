@@ -28,6 +28,7 @@ run selftest_pairs32_tma OTB_GEMM2_MIN_PAIRS=32 OTB_GEMM_EPI_TMA=1 -- build/self
 # 2. parity suites with the candidates switched on (kernel tests first: they localise a failure)
 run pytest_kernels_tma OTB_GEMM_EPI_TMA=1 -- python -m pytest tests/test_kernels_gpu.py -m gpu -x -q
 run pytest_kernels_lnfused OTB_LN_FUSED=1 -- python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "layernorm or ln"
+run pytest_multicast -- python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k multi_tensor_cast
 run pytest_modules_all OTB_GEMM_EPI_TMA=1 OTB_LN_FUSED=1 -- python -m pytest tests/test_modules_gpu.py -m gpu -x -q
 
 # 3. step-level A/B (same box, back to back)
@@ -36,7 +37,8 @@ run bench_default -- $B
 run bench_epi_tma OTB_GEMM_EPI_TMA=1 -- $B
 run bench_lnfused OTB_LN_FUSED=1 -- $B
 run bench_pairs32 OTB_GEMM2_MIN_PAIRS=32 -- $B
-run bench_all OTB_GEMM_EPI_TMA=1 OTB_LN_FUSED=1 OTB_GEMM2_MIN_PAIRS=32 -- $B
+run bench_multicast OTB_MULTI_CAST=1 -- $B
+run bench_all OTB_GEMM_EPI_TMA=1 OTB_LN_FUSED=1 OTB_GEMM2_MIN_PAIRS=32 OTB_MULTI_CAST=1 -- $B
 run bench_default_again -- $B
 grep -h '"metric"' "$out"/bench_*.log | python -c "
 import sys, json
