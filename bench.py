@@ -191,7 +191,8 @@ def run_cuda(args):
     batch = args.per_gpu_batch
     clip, perceiver, gated = build_modules(dev)
     trainable = list(perceiver.parameters()) + list(gated.parameters())
-    flat = FlatGradBuffer(trainable, device=dev)
+    comm_dtype = torch.bfloat16 if args.grad_comm_dtype == "bf16" else None
+    flat = FlatGradBuffer(trainable, device=dev, comm_dtype=comm_dtype, nccl_registered=args.nccl_registered and world > 1)
     h_vis, h_hid, h_loc = host_batch(batch, rank)
     d_vis, d_hid, d_loc = h_vis.to(dev), h_hid.to(dev), h_loc.to(dev)
     B, L, D = batch, CFG["L"], CFG["D"]
@@ -243,7 +244,7 @@ def run_cuda(args):
         run_clip()
         if work is not None:
             work.wait()
-            if dist.get_backend() == "gloo":
+            if dist.get_backend() == "gloo" and not getattr(work, "averaged", False):
                 flat.flat.div_(world)
         return loss
 
@@ -357,7 +358,8 @@ def run_cuda(args):
                              "with the CLIP forward of the next batch" if world > 1 else ""),
                    "weights": "fp32 master, bf16 compute copies re-cast every step; fp32 grads in one flat buffer",
                    "cache": "per-step working set (2.4 GB bf16 weights + activations) >> 126 MB L2; no explicit flush",
-                   "grad_allreduce_bytes": flat.nbytes() if world > 1 else 0},
+                   "grad_allreduce_bytes": flat.comm_nbytes() if world > 1 else 0,
+                   "grad_allreduce_dtype": args.grad_comm_dtype, "nccl_registered_buffer": bool(args.nccl_registered)},
         "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": (h_vis.numel() * 2 + h_hid.numel() * 2 + h_loc.numel()) * 1,
                 "d2h_bytes_per_step": 4},
@@ -485,6 +487,11 @@ def main():
     ap.add_argument("--per-gpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--grad-comm-dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="wire format of the single gradient all-reduce (gradients stay fp32 on both sides); bf16 "
+                         "halves the payload to SURVEY.md §8e's 2.36 GB at the cost of two cast passes per step")
+    ap.add_argument("--nccl-registered", action="store_true",
+                    help="allocate the flat gradient buffer from NCCL's allocator and register it (zero-copy / NVLS)")
     ap.add_argument("--seq-len", type=int, default=256, help="text length L (SURVEY.md §8d sweeps 128/256/512/1024)")
     args = ap.parse_args()
     CFG["L"] = args.seq_len

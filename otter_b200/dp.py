@@ -11,8 +11,25 @@ import torch
 import torch.distributed as dist
 
 
+class _CommHandle:
+    """Completion handle of a reduced-precision all-reduce: wait() also copies the averaged gradients back into
+    the fp32 buffer the `.grad` views alias."""
+    averaged = True
+
+    def __init__(self, owner, work, divide_by):
+        self.owner, self.work, self.divide_by = owner, work, divide_by
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+        if self.divide_by:
+            self.owner.comm.div_(self.divide_by)
+        self.owner.flat.copy_(self.owner.comm)
+        return True
+
+
 class FlatGradBuffer:
-    def __init__(self, params, device=None, dtype=torch.float32):
+    def __init__(self, params, device=None, dtype=torch.float32, comm_dtype=None, nccl_registered=False):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -23,7 +40,14 @@ class FlatGradBuffer:
             self.offsets.append(off)
             off += (p.numel() + 3) // 4 * 4
         self.numel = off
-        self.flat = torch.zeros(off, device=device, dtype=dtype)
+        self._pools = []
+        self._registered = bool(nccl_registered)
+        self.flat = self._alloc(off, dtype, device)
+        # optional wire format of the collective (SURVEY.md §8e budgets the bf16 payload: 2.36 GB instead of 4.72 GB);
+        # gradients are still produced, accumulated and handed to the optimizer in `dtype`
+        self.comm = None
+        if comm_dtype is not None and comm_dtype != dtype:
+            self.comm = self._alloc(off, comm_dtype, device)
         for p, o in zip(self.params, self.offsets):
             view = self.flat[o:o + p.numel()].view(p.shape)
             if p.dtype != dtype:
@@ -32,6 +56,22 @@ class FlatGradBuffer:
             if dtype == torch.float32:
                 p._otb_grad = view          # sink used by otter_b200 backward kernels
                 p._otb_grad_live = False
+
+    def _alloc(self, n, dtype, device):
+        """Plain zero-filled allocation, or (nccl_registered=True) one drawn from NCCL's own allocator and registered
+        with the communicator, so the collective can run zero-copy / in-switch (NVLS) on the user buffer instead of
+        staging through NCCL's internal buffers.  Needs an initialised NCCL process group; fails loudly otherwise."""
+        if not self._registered:
+            return torch.zeros(n, device=device, dtype=dtype)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl":
+            raise RuntimeError("nccl_registered=True needs an initialised NCCL process group")
+        backend = dist.distributed_c10d._get_default_group()._get_backend(torch.device(device))
+        pool = torch.cuda.MemPool(backend.mem_allocator)
+        with torch.cuda.use_mem_pool(pool):
+            t = torch.zeros(n, device=device, dtype=dtype)
+        backend.register_mem_pool(pool)
+        self._pools.append(pool)              # keep the pool (and the registration) alive with the buffer
+        return t
 
     def begin_step(self):
         """Start a step.  Parameters whose gradients are written by otter_b200 kernels (`_otb_sink_user`, learned
@@ -54,6 +94,18 @@ class FlatGradBuffer:
         """The one collective of the step: mean over ranks (DDP semantics)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
+        if self.comm is not None:
+            self.comm.copy_(self.flat)                 # cast on the current stream, ahead of the collective
+            if dist.get_backend(group) == "gloo":
+                w = dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+                h = _CommHandle(self, w if async_op else None, dist.get_world_size(group))
+            else:
+                w = dist.all_reduce(self.comm, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+                h = _CommHandle(self, w if async_op else None, 0)
+            if not async_op:
+                h.wait()
+                return None
+            return h
         if dist.get_backend(group) == "gloo":          # gloo has no AVG
             w = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
             if not async_op:
@@ -66,6 +118,11 @@ class FlatGradBuffer:
 
     def nbytes(self):
         return self.flat.numel() * self.flat.element_size()
+
+    def comm_nbytes(self):
+        """Bytes each rank contributes to the step's all-reduce."""
+        buf = self.comm if self.comm is not None else self.flat
+        return buf.numel() * buf.element_size()
 
 
 def shard_batch(global_batch, rank, world_size):

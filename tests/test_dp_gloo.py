@@ -18,13 +18,13 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, comm_dtype=None, async_op=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(0)                                   # identical weights on all ranks
     lin = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
     lin[0].bias.requires_grad_(False)                      # a frozen parameter must be skipped
-    flat = FlatGradBuffer(lin.parameters(), device="cpu")
+    flat = FlatGradBuffer(lin.parameters(), device="cpu", comm_dtype=comm_dtype)
     assert flat.numel % 4 == 0 and all(o % 4 == 0 for o in flat.offsets)
     g = torch.Generator().manual_seed(7)
     X = torch.randn(8, 6, generator=g)                     # the GLOBAL batch, same on both ranks
@@ -33,28 +33,47 @@ def _worker(rank, world, port, q):
     loss = lin(X[lo:hi]).pow(2).mean()
     loss.backward()                                        # autograd accumulates into the flat views
     flat.finish_step()
-    flat.all_reduce()
+    work = flat.all_reduce(async_op=async_op)
+    if work is not None:
+        work.wait()
+        if not getattr(work, "averaged", False):
+            flat.flat.div_(world)
     # reference: full-batch gradient on one process (equal shards => mean of shard grads == full-batch grad)
     ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
     ref.load_state_dict(lin.state_dict())
     ref(X).pow(2).mean().backward()
-    ok = all(torch.allclose(p.grad, r.grad, rtol=1e-5, atol=1e-6)
+    rtol, atol = (1e-5, 1e-6) if comm_dtype is None else (2e-2, 2e-3)       # bf16 wire format: 8 mantissa bits
+    ok = all(torch.allclose(p.grad, r.grad, rtol=rtol, atol=atol)
              for p, r in zip(lin.parameters(), ref.parameters()) if p.requires_grad)
     views_ok = all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in flat.params)
     q.put((rank, ok, views_ok, flat.numel))
     dist.destroy_process_group()
 
 
-def test_flat_allreduce_world2():
+def _run_world2(*extra):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q) + extra) for r in range(2)]
     [p.start() for p in procs]
     res = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(timeout=60) for p in procs]
     assert all(ok and views for _, ok, views, _ in res), res
     assert res[0][3] == res[1][3]
+
+
+def test_flat_allreduce_world2():
+    _run_world2()
+
+
+def test_flat_allreduce_world2_async():
+    _run_world2(None, True)
+
+
+def test_flat_allreduce_world2_bf16_wire():
+    """Reduced-precision wire format (SURVEY.md §8e's 2.36 GB payload): gradients stay fp32 on both sides."""
+    _run_world2(torch.bfloat16, False)
+    _run_world2(torch.bfloat16, True)
 
 
 def test_shard_batch_partitions_exactly():
