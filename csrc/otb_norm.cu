@@ -299,6 +299,34 @@ __global__ void ln_bwd_finalize_kernel(const float* __restrict__ ws, float* __re
   if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + b;
 }
 
+// Wide finalize for the one-pass kernel's [2][chunks][D] partials (chunks up to one per SM): a CTA owns 32 columns,
+// its 8 thread rows stride over the chunks (coalesced 128 B reads), then a fixed-order smem reduction (deterministic).
+__global__ void __launch_bounds__(256)
+ln_bwd_finalize_wide_kernel(const float* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int D,
+                            int chunks, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float sg[8][32], sb[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float g = 0.f, b = 0.f;
+  if (c < D) {
+    for (int k = threadIdx.y; k < chunks; k += 8) {
+      g += ws[static_cast<long long>(k) * D + c];
+      b += ws[(static_cast<long long>(chunks) + k) * D + c];
+    }
+  }
+  sg[threadIdx.y][threadIdx.x] = g;
+  sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) { tg += sg[y][threadIdx.x]; tb += sb[y][threadIdx.x]; }
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + tg;
+    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + tb;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // text_time (integer, bit-exact)  modeling_otter.py:296-311 — one thread per batch row (L <= few K)
 // ------------------------------------------------------------------------------------------------
@@ -697,8 +725,8 @@ extern "C" int otb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, in
     OTB_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(256), 0, ST(stream), static_cast<const bf16*>(dy), lddy,
                             static_cast<const bf16*>(x), ldx, mean, rstd, gamma, static_cast<const bf16*>(add), ldadd,
                             static_cast<bf16*>(dx), lddx, ws, rows, D));
-    OTB_CHECK_CUDA(launch_k(ln_bwd_finalize_kernel, dim3((D + 255) / 256), dim3(256), 0, ST(stream), ws, dgamma, dbeta, D,
-                            grid, accumulate));
+    OTB_CHECK_CUDA(launch_k(ln_bwd_finalize_wide_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, ST(stream), ws, dgamma,
+                            dbeta, D, grid, accumulate));
     count_launch(2);
     OTB_CHECK_CUDA(cudaGetLastError());
     return OTB_OK;
