@@ -38,10 +38,11 @@ run bench_epi_tma OTB_GEMM_EPI_TMA=1 -- $B
 run bench_lnfused OTB_LN_FUSED=1 -- $B
 run bench_pairs32 OTB_GEMM2_MIN_PAIRS=32 -- $B
 run bench_multicast OTB_MULTI_CAST=1 -- $B
+run bench_e2e_prefetch -- $B --e2e-prefetch
 run bench_all OTB_GEMM_EPI_TMA=1 OTB_LN_FUSED=1 OTB_GEMM2_MIN_PAIRS=32 OTB_MULTI_CAST=1 -- $B
 run bench_default_again -- $B
 grep -h '"metric"' "$out"/bench_*.log | python -c "
 import sys, json
 for l in sys.stdin:
-    d = json.loads(l); print(d['value'], d['ms_per_step'], d['roofline']['frac'])
+    d = json.loads(l); print(d['value'], d['ms_per_step'], d['roofline']['frac'], 'e2e', d['e2e']['value'])
 "
