@@ -121,7 +121,14 @@ static int run_case(const Case& c) {
 
   double max_err = 0, max_ref = 0, max_aux_err = 0;
   size_t bad = 0;
-  for (int m = 0; m < M; ++m)
+  // Big problems are verified on a subset of rows (all columns): the first / last rows, every row next to a 128-row
+  // tile boundary, and a stride of the rest — the host reference is a scalar triple loop.
+  const bool sample_rows = (double)M * N * K > 3e9;
+  for (int m = 0; m < M; ++m) {
+    if (sample_rows) {
+      const int r = m % 128;
+      if (!(m < 4 || m >= M - 4 || r < 2 || r >= 126 || m % 61 == 0)) continue;
+    }
     for (int n = 0; n < N; ++n) {
       double acc = 0;
       const float* a = &A[(size_t)m * K];
@@ -153,6 +160,7 @@ static int run_case(const Case& c) {
         if (!(ae <= fabs(pre) * 8e-3 + 2e-3)) ++bad;
       }
     }
+  }
   printf("  M=%d N=%d K=%d a_mn=%d b_mn=%d mode=%d : max_err=%.3e (max|ref|=%.3f aux_err=%.3e) bad=%zu %s\n", M, N, K,
          c.a_mn, c.b_mn, c.mode, max_err, max_ref, max_aux_err, bad, bad ? "FAIL" : "ok");
   cudaFree(dA); cudaFree(dB); cudaFree(dres); cudaFree(dauxin); cudaFree(dauxout); cudaFree(dout_bf);
