@@ -1,6 +1,7 @@
 #!/usr/bin/env bash
 # Round-2 first GPU call: validate and A/B the opt-in candidates of branch r2-prep in ONE gpurun.
-#   gpurun --timeout 1500 -- 'bash tools/r2_sweep.sh'
+#   git merge r2-prep   (on main: .worktrees/ is not shipped to the GPU box), then
+#   gpurun --timeout 1800 -- 'bash tools/r2_sweep.sh'
 # Everything lands in gpurun_out/r2_sweep/.  Each step runs under its own timeout so a hang in a candidate
 # (mbarrier waits trap after 2 s) cannot eat the call.
 set -u
@@ -14,7 +15,7 @@ run() {  # name, env assignments..., -- command
   while [ "$1" != "--" ]; do envs+=("$1"); shift; done
   shift
   echo "=== $name (${envs[*]:-default})"
-  env "${envs[@]}" timeout 300 "$@" > "$out/$name.log" 2> "$out/$name.err"
+  env "${envs[@]}" timeout "${TMO:-300}" "$@" > "$out/$name.log" 2> "$out/$name.err"
   echo "    exit $?"
   tail -n 3 "$out/$name.log"
 }
@@ -30,6 +31,9 @@ run pytest_kernels_tma OTB_GEMM_EPI_TMA=1 -- python -m pytest tests/test_kernels
 run pytest_kernels_lnfused OTB_LN_FUSED=1 -- python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "layernorm or ln"
 run pytest_multicast -- python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k multi_tensor_cast
 run pytest_modules_all OTB_GEMM_EPI_TMA=1 OTB_LN_FUSED=1 -- python -m pytest tests/test_modules_gpu.py -m gpu -x -q
+
+# the default path again after the merge (the kernels were re-templated): full GPU suite, no knobs
+TMO=600 run pytest_default_full -- python -m pytest tests -m gpu -x -q
 
 # 3. step-level A/B (same box, back to back)
 B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline"
