@@ -108,6 +108,8 @@ int otb_abi_sizeof(int which) {
     case 0: return (int)sizeof(otb_gemm_epilogue);
     case 1: return (int)sizeof(otb_attn_desc);
     case 2: return (int)sizeof(otb_attn_grads);
+    case 3: return (int)sizeof(otb_lm_attn_desc);
+    case 4: return (int)sizeof(otb_lm_attn_grads);
     default: return -1;
   }
 }

@@ -32,6 +32,9 @@ run pytest_kernels_lnfused OTB_LN_FUSED=1 -- python -m pytest tests/test_kernels
 run pytest_multicast -- python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k multi_tensor_cast
 run pytest_modules_all OTB_GEMM_EPI_TMA=1 OTB_LN_FUSED=1 -- python -m pytest tests/test_modules_gpu.py -m gpu -x -q
 
+# §8f rank-1 candidate (new kernels, nothing else depends on them): run last among the parity suites
+run pytest_lm -- python -m pytest tests/test_lm_gpu.py -m gpu -x -q
+
 # the default path again after the merge (the kernels were re-templated): full GPU suite, no knobs
 TMO=600 run pytest_default_full -- python -m pytest tests -m gpu -x -q
 
