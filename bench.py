@@ -206,7 +206,10 @@ def run_cuda(args):
     def train_step(hidden, hid, loc):
         """perceiver + 8 gated blocks forward/backward on precomputed CLIP features."""
         # weights "just updated by the optimizer": re-derive the bf16 compute copies (autocast-equivalent work)
-        P.invalidate(trainable)
+        if os.environ.get("OTB_MULTI_CAST") == "1":       # candidate: one multi-tensor launch instead of 67 casts
+            P.refresh(trainable)
+        else:
+            P.invalidate(trainable)
         flat.begin_step()
         media = MediaFromClipFn.apply(hidden, perceiver.frame_embs, CFG["F"])            # drop CLS (+frame_embs)
         media = perceiver.resample_media(media, B * CFG["T"])                              # [B*T*64, 1024] bf16

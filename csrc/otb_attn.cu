@@ -118,7 +118,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* bar_s = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int qt = blockIdx.x, h = blockIdx.y, prob = blockIdx.z;
 
   if (tid == 32) {

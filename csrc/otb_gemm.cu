@@ -27,6 +27,8 @@ namespace otb {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kGemmThreads = 384;   // 8 epilogue warps + 4 control warps
+constexpr int kEpiWarpStage = 32 * 128;             // one epilogue warp's store stage: 32 rows x 128 B (64 bf16 columns)
+constexpr int kEpiStageBytes = 8 * kEpiWarpStage;    // 32 KB, sits between the operand ring and the barriers
 
 struct GemmEpi {
   const float* bias;
@@ -39,6 +41,7 @@ struct GemmEpi {
   int act, scale_tanh, out_fp32, accumulate;
   float alpha;
   int res_fp32;   // residual is fp32 [M][N] (fp32-grade parity path)
+  int tma_out;    // bf16 output leaves through a swizzled smem stage + TMA store (full 128 B lines, bounds clipped by TMA)
 };
 
 template <int BN>
@@ -154,18 +157,134 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, float scale, ui
   }
 }
 
+// TMA-store variant of the epilogue.  The direct epilogue above has every thread write 16 B pieces of its own row:
+// 32 different 128 B lines per warp store instruction, partially written sectors on the way to L2, and the
+// accumulate class first READS its old fp32 values the same way.  Here a warp assembles 32 rows x 128 B (64 bf16 or
+// 32 fp32 columns) in a SWIZZLE_128B smem stage — thread = row, the 16 B unit j of row r lands at unit j ^ (r & 7),
+// which is bank-conflict free and exactly the layout the output tensor map expects — and one lane hands the 4 KB box
+// to the TMA engine, which writes whole lines, clips rows >= M / columns >= N, and for `accumulate` performs the
+// fp32 add at L2 (cp.reduce.async.bulk ... add) so the old values never travel to the SM.
+// The stage is reused once the previous bulk operation has finished READING it (wait_group.read), which overlaps
+// with the TMEM load and the math of the next chunk.  The pre-activation side output (aux_out) keeps direct stores.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, float scale, uint32_t taddr, int m0, int n0, int M,
+                                                  int N, int q, int half, int lane, uint8_t* stage,
+                                                  const CUtensorMap* map_d) {
+  const int row0 = m0 + q * 32;
+  if (row0 >= M) return;                                      // warp-uniform: no row of this quarter is inside
+  const int row = row0 + lane;
+  const bool row_ok = row < M;
+  const long long lrow = row;
+  uint8_t* my_row = stage + lane * 128;
+  const int xr = lane & 7;
+#pragma unroll 1
+  for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {     // 32-column chunks of this warp's half
+    const int colbase = n0 + c * 32;
+    if (colbase >= N) break;                                  // warp-uniform
+    const bool act_chunk = row_ok;
+    uint4 res[4], aux[4];
+    if (act_chunk) {
+      if (ep.residual != nullptr) {
+        const uint4* pr = reinterpret_cast<const uint4*>(ep.residual + lrow * ep.ld_res + colbase);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) res[g] = __ldg(pr + g);
+      }
+      if (ep.aux_in != nullptr) {
+        const uint4* pa = reinterpret_cast<const uint4*>(ep.aux_in + lrow * ep.ld_aux_in + colbase);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) aux[g] = __ldg(pa + g);
+      }
+    }
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    tmem_ld_wait();
+    // bf16: two chunks share one 128 B-wide box (units 0-3 / 4-7); fp32: one chunk is one box (units 0-7).
+    const bool first_of_box = ep.out_fp32 || (c & 1) == 0;
+    const bool last_of_box = ep.out_fp32 || (c & 1) == 1 || colbase + 32 >= N;
+    if (first_of_box) {                                       // the previous box must have left the stage
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = colbase + g * 8;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+      if (act_chunk && col < N) {
+        if (ep.bias != nullptr) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (ep.aux_out != nullptr) {
+          uint4 x;
+          x.x = pack_bf16x2(v[0], v[1]); x.y = pack_bf16x2(v[2], v[3]);
+          x.z = pack_bf16x2(v[4], v[5]); x.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(ep.aux_out + lrow * ep.ld_aux_out + col) = x;
+        }
+        if (ep.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
+        } else if (ep.act == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
+        }
+        if (ep.aux_in != nullptr) {
+          const float2 a0 = unpack_bf16x2(aux[g].x), a1 = unpack_bf16x2(aux[g].y), a2 = unpack_bf16x2(aux[g].z),
+                       a3 = unpack_bf16x2(aux[g].w);
+          v[0] *= gelu_grad_fast(a0.x); v[1] *= gelu_grad_fast(a0.y);
+          v[2] *= gelu_grad_fast(a1.x); v[3] *= gelu_grad_fast(a1.y);
+          v[4] *= gelu_grad_fast(a2.x); v[5] *= gelu_grad_fast(a2.y);
+          v[6] *= gelu_grad_fast(a3.x); v[7] *= gelu_grad_fast(a3.y);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= scale;
+        if (ep.residual != nullptr) {
+          const float2 a0 = unpack_bf16x2(res[g].x), a1 = unpack_bf16x2(res[g].y), a2 = unpack_bf16x2(res[g].z),
+                       a3 = unpack_bf16x2(res[g].w);
+          v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
+          v[4] += a2.x; v[5] += a2.y; v[6] += a3.x; v[7] += a3.y;
+        }
+      }
+      // rows >= M and columns >= N hold don't-care values: the TMA engine clips them
+      if (ep.out_fp32) {
+        *reinterpret_cast<float4*>(my_row + (((2 * g) ^ xr) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(my_row + (((2 * g + 1) ^ xr) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(my_row + ((((c & 1) * 4 + g) ^ xr) << 4)) = o;
+      }
+    }
+    if (last_of_box) {
+      fence_proxy_async_smem();                               // generic-proxy writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        const int box_col = ep.out_fp32 ? colbase : (colbase & ~63);
+        if (ep.accumulate) tma_reduce_add_2d(map_d, stage, box_col, row0);
+        else tma_store_2d(map_d, stage, box_col, row0);
+        tma_store_commit();
+      }
+    }
+  }
+}
+
 // MC = true: clusters of 2 CTAs work on two vertically adjacent 128-row tiles of the same BN-wide column block;
 // each CTA fetches half of the shared B tile and TMA-multicasts it to both, which cuts the L2->SM operand
 // traffic per FLOP by a third (the big GEMMs are L2-bandwidth bound at one 128xBN tile per CTA).
-template <int BN, bool A_MN, bool B_MN, bool MC>
+template <int BN, bool A_MN, bool B_MN, bool MC, bool TS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
-                 int K, GemmEpi ep) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_d, int M, int N, int K, GemmEpi ep) {
   using Cfg = GemmCfg<BN>;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* epi_stage = smem + Cfg::kStages * Cfg::kStageBytes;      // 8 x 4 KB (1024-aligned), TMA-store epilogue only
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + (TS ? kEpiStageBytes : 0));
   uint64_t* full_bar = bars;                        // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;    // [2]
@@ -296,12 +415,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int n0 = (t / tiles_m) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(ep, scale, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, m0, n0, M, N, q, half,
-                        lane);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if constexpr (TS)
+        epilogue_tile_tma<BN>(ep, scale, taddr, m0, n0, M, N, q, half, lane, epi_stage + warp * kEpiWarpStage, &map_d);
+      else
+        epilogue_tile<BN>(ep, scale, taddr, m0, n0, M, N, q, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (TS && lane == 0) tma_store_wait_read<0>();   // the stage must outlive the last bulk store's reads
   }
 
   tc_fence_before();
@@ -313,7 +436,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool MC>
+template <int BN, bool A_MN, bool B_MN, bool MC, bool TS>
 static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                        const GemmEpi& ep, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -325,10 +448,17 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   if (!B_MN) rc = make_tmap_bf16_2d(&mb, B, N, K, ldb, MC ? BN / 2 : BN, 64);
   else       rc = make_tmap_bf16_2d(&mb, B, K, N, ldb, kBK, 64);
   if (rc) return rc;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MC>;
+  CUtensorMap md = ma;                                               // placeholder when the direct epilogue is used
+  if (TS) {                                                          // [M][N] output, box 32 rows x 128 B
+    rc = ep.out_fp32 ? make_tmap_f32_2d(&md, ep.out, M, N, ep.ld_out, 32, 32)
+                     : make_tmap_bf16_2d(&md, ep.out, M, N, ep.ld_out, 32, 64);
+    if (rc) return rc;
+  }
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MC, TS>;
+  constexpr int smem_bytes = Cfg::kSmemBytes + (TS ? kEpiStageBytes : 0);
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    OTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + BN - 1) / BN;
@@ -354,9 +484,9 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
   cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  OTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, ep));
+  OTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, md, M, N, K, ep));
   count_launch();
   return OTB_OK;
 }
@@ -374,15 +504,16 @@ constexpr int k2Stages = 6;
 constexpr int k2StageBytes = 2 * 128 * kBK * 2;   // A 16 KB + B-half 16 KB
 constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool TS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
-                  int K, GemmEpi ep) {
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_d, int M, int N, int K, GemmEpi ep) {
   constexpr int BN = 256;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+  uint8_t* epi_stage = smem + k2Stages * k2StageBytes;              // 8 x 4 KB (1024-aligned), TMA-store epilogue only
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + (TS ? kEpiStageBytes : 0));
   uint64_t* full_bar = bars;                    // [k2Stages]  (leader's copy is the live one)
   uint64_t* empty_bar = bars + k2Stages;        // [k2Stages]  (both CTAs)
   uint64_t* tfull_bar = bars + 2 * k2Stages;    // [2]         (both CTAs)
@@ -485,12 +616,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int n0 = (pt / tiles_mp) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(ep, scale, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, m0, n0, M, N, q, half,
-                        lane);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if constexpr (TS)
+        epilogue_tile_tma<BN>(ep, scale, taddr, m0, n0, M, N, q, half, lane, epi_stage + warp * kEpiWarpStage, &map_d);
+      else
+        epilogue_tile<BN>(ep, scale, taddr, m0, n0, M, N, q, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);      // leader's barrier
     }
+    if (TS && lane == 0) tma_store_wait_read<0>();   // the stage must outlive the last bulk store's reads
   }
 
   tc_fence_before();
@@ -502,7 +637,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool TS>
 static int launch_gemm2(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                         const GemmEpi& ep, cudaStream_t stream) {
   CUtensorMap ma, mb;
@@ -513,10 +648,17 @@ static int launch_gemm2(const void* A, long long lda, const void* B, long long l
   if (!B_MN) rc = make_tmap_bf16_2d(&mb, B, N, K, ldb, 128, 64);
   else       rc = make_tmap_bf16_2d(&mb, B, K, N, ldb, kBK, 64);
   if (rc) return rc;
-  auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
+  CUtensorMap md = ma;
+  if (TS) {
+    rc = ep.out_fp32 ? make_tmap_f32_2d(&md, ep.out, M, N, ep.ld_out, 32, 32)
+                     : make_tmap_bf16_2d(&md, ep.out, M, N, ep.ld_out, 32, 64);
+    if (rc) return rc;
+  }
+  auto kern = gemm2_bf16_kernel<A_MN, B_MN, TS>;
+  constexpr int smem_bytes = k2SmemBytes + (TS ? kEpiStageBytes : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+    OTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   const int num_pt = ((M + 255) / 256) * ((N + 255) / 256);
@@ -534,11 +676,11 @@ static int launch_gemm2(const void* A, long long lda, const void* B, long long l
   ++nattr;
   cfg.gridDim = dim3(2 * (num_pt < max_clusters ? num_pt : max_clusters));
   cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = k2SmemBytes;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
-  OTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, M, N, K, ep));
+  OTB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, md, M, N, K, ep));
   count_launch();
   return OTB_OK;
 }
@@ -575,6 +717,10 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   ep.alpha = e->alpha;
   ep.res_fp32 = e->res_fp32;
   OTB_CHECK_ARG(!e->res_fp32 || e->out_fp32, "otb_gemm_bf16: fp32 residual requires fp32 output");
+  // OTB_GEMM_EPI_TMA=1: bf16 outputs leave through the smem-staged TMA-store epilogue (candidate, off by default)
+  static const bool epi_tma = [] { const char* v = getenv("OTB_GEMM_EPI_TMA"); return v && v[0] == '1'; }();
+  ep.tma_out = (epi_tma && !e->res_fp32 && (reinterpret_cast<uintptr_t>(e->out) & 15) == 0 &&
+                (!e->out_fp32 || e->ld_out % 4 == 0)) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // Tile-N choice: 256-wide tiles unless that leaves most SMs idle.  CTA-pair multicast (MC) when there are at
@@ -588,17 +734,28 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   // cta_group::2 pair kernel for the large problems (>= one 256x256 pair tile per SM pair)
   static const int two_cta = [] { const char* e = getenv("OTB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
-  if (two_cta && !bn128 && ((M + 255) / 256) * ((N + 255) / 256) >= sm_count() / 2) {
+  // OTB_GEMM2_MIN_PAIRS: smallest number of 256x256 pair tiles that goes to the pair kernel (default: one per SM pair)
+  static const int min_pairs = [] { const char* v = getenv("OTB_GEMM2_MIN_PAIRS"); return v ? atoi(v) : 0; }();
+  const int pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  const bool pair_ok = min_pairs > 0 ? (pair_tiles >= min_pairs && N >= 256 && M > 128) : (!bn128 && pair_tiles >= sm_count() / 2);
+  if (two_cta && pair_ok) {
+#define OTB_GEMM2_CASE(A_, B_)                                                        \
+  return ep.tma_out ? launch_gemm2<A_, B_, true>(A, lda, B, ldb, M, N, K, ep, st)     \
+                    : launch_gemm2<A_, B_, false>(A, lda, B, ldb, M, N, K, ep, st)
     switch (sel) {
-      case 0: return launch_gemm2<false, false>(A, lda, B, ldb, M, N, K, ep, st);
-      case 1: return launch_gemm2<false, true>(A, lda, B, ldb, M, N, K, ep, st);
-      case 3: return launch_gemm2<true, true>(A, lda, B, ldb, M, N, K, ep, st);
+      case 0: OTB_GEMM2_CASE(false, false);
+      case 1: OTB_GEMM2_CASE(false, true);
+      case 3: OTB_GEMM2_CASE(true, true);
       default: break;
     }
+#undef OTB_GEMM2_CASE
   }
 #define OTB_GEMM_CASE(BN_, A_, B_)                                                                   \
-  return mc ? launch_gemm<BN_, A_, B_, true>(A, lda, B, ldb, M, N, K, ep, st)                         \
-            : launch_gemm<BN_, A_, B_, false>(A, lda, B, ldb, M, N, K, ep, st)
+  if (ep.tma_out)                                                                                     \
+    return mc ? launch_gemm<BN_, A_, B_, true, true>(A, lda, B, ldb, M, N, K, ep, st)                 \
+              : launch_gemm<BN_, A_, B_, false, true>(A, lda, B, ldb, M, N, K, ep, st);               \
+  return mc ? launch_gemm<BN_, A_, B_, true, false>(A, lda, B, ldb, M, N, K, ep, st)                  \
+            : launch_gemm<BN_, A_, B_, false, false>(A, lda, B, ldb, M, N, K, ep, st)
   if (bn128) {
     switch (sel) {
       case 0: OTB_GEMM_CASE(128, false, false);

@@ -60,6 +60,27 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   return OTB_OK;
 }
 
+int make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(OTB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(OTB_ERR_INVALID, "TMA base not 16B aligned");
+  if ((ld * 4) % 16 != 0) return set_error(OTB_ERR_INVALID, "TMA row pitch %llu fp32 elements not a multiple of 4",
+                                            (unsigned long long)ld);
+  if (box_cols * 4 != 128 || box_rows > 256) return set_error(OTB_ERR_INVALID, "bad TMA box");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(OTB_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
+                     (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+  return OTB_OK;
+}
+
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("OTB_PDL"); return (e && e[0] == '1'); }();
   return on;
@@ -87,6 +108,8 @@ int otb_abi_sizeof(int which) {
     case 0: return (int)sizeof(otb_gemm_epilogue);
     case 1: return (int)sizeof(otb_attn_desc);
     case 2: return (int)sizeof(otb_attn_grads);
+    case 3: return (int)sizeof(otb_lm_attn_desc);
+    case 4: return (int)sizeof(otb_lm_attn_grads);
     default: return -1;
   }
 }

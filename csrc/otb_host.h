@@ -30,6 +30,10 @@ void count_launch(int n = 1);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
 
+// Same for an fp32 tensor (box_cols * 4 bytes must be 128): output maps of the TMA-store / reduce-add epilogue.
+int make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols);
+
 int sm_count();
 bool pdl_enabled();   // OTB_PDL=1 enables programmatic dependent launch (measured neutral under graph replay; off by default)
 

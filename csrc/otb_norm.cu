@@ -1,6 +1,8 @@
 // otter_b200 — HBM-bound passes of the hot path: LayerNorm fwd/bwd, mask index construction,
 // casts, broadcast / grouped reductions, tanh-gate gradient, CLIP embedding assembly, Fuyu scatter.
 // All are plain coalesced, 16-byte-vectorised CUDA kernels (no tensor cores: byte/element work).
+#include <cstdlib>
+
 #include "otb_common.cuh"
 #include "otb_host.h"
 
@@ -156,6 +158,132 @@ ln_bwd_param_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __r
     if (gc < D) ws[(static_cast<long long>(which) * chunks + chunk) * D + gc] = acc;
   }
 }
+// One-pass LayerNorm backward (candidate, OTB_LN_FUSED=1): dx AND the gamma/beta column partials from a single read of
+// x / dy.  A CTA walks its rows in batches of kLnR; thread t owns the 16 B column vectors t, t+256, ... (VPT of them) of
+// every row, so the parameter partials stay in its registers across all rows of the CTA (deterministic: fixed order,
+// no atomics) and the two row statistics of a batch take one block reduction (double-buffered smem, one barrier).
+// ws layout is the one ln_bwd_finalize_kernel reads: [2][gridDim.x][D].
+constexpr int kLnR = 4;
+template <int VPT>
+__global__ void __launch_bounds__(256)
+ln_bwd_fused_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ x, long long ldx,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const bf16* __restrict__ add, long long ldadd, bf16* __restrict__ dx, long long lddx,
+                    float* __restrict__ ws, int rows, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[2][8][2 * kLnR];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  float gam[VPT][8], pg[VPT][8], pb[VPT][8];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int v = threadIdx.x + j * 256;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { pg[j][i] = 0.f; pb[j][i] = 0.f; gam[j][i] = 0.f; }
+    if (v < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+      gam[j][0] = g0.x; gam[j][1] = g0.y; gam[j][2] = g0.z; gam[j][3] = g0.w;
+      gam[j][4] = g1.x; gam[j][5] = g1.y; gam[j][6] = g1.z; gam[j][7] = g1.w;
+    }
+  }
+  const int nbatch = (rows + kLnR - 1) / kLnR;
+  int parity = 0;
+  for (int b = blockIdx.x; b < nbatch; b += gridDim.x, parity ^= 1) {
+    const int r0 = b * kLnR;
+    uint4 ux[kLnR][VPT], ud[kLnR][VPT];
+    float mu[kLnR], rs[kLnR];
+#pragma unroll
+    for (int r = 0; r < kLnR; ++r) {
+      const int row = r0 + r;
+      const bool ok = row < rows;
+      mu[r] = ok ? __ldg(mean + row) : 0.f;
+      rs[r] = ok ? __ldg(rstd + row) : 0.f;
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        const int v = threadIdx.x + j * 256;
+        ux[r][j] = make_uint4(0u, 0u, 0u, 0u);
+        ud[r][j] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok && v < nvec) {
+          ux[r][j] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx) + v);
+          ud[r][j] = __ldg(reinterpret_cast<const uint4*>(dy + static_cast<long long>(row) * lddy) + v);
+        }
+      }
+    }
+    // per-row sums of g = dy*gamma and g*xhat, and the column partials (dgamma += dy*xhat, dbeta += dy)
+    float s[2 * kLnR];
+#pragma unroll
+    for (int r = 0; r < kLnR; ++r) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        float fx[8], fd[8];
+        unpack8(ux[r][j], fx);
+        unpack8(ud[r][j], fd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (fx[i] - mu[r]) * rs[r];         // rows >= `rows` and vectors >= nvec hold zeros (rs = 0)
+          const float g = fd[i] * gam[j][i];
+          s1 += g;
+          s2 += g * xh;
+          pg[j][i] += fd[i] * xh;
+          pb[j][i] += fd[i];
+        }
+      }
+      s[2 * r] = warp_sum(s1);
+      s[2 * r + 1] = warp_sum(s2);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 2 * kLnR; ++k) red[parity][warp][k] = s[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2 * kLnR; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[parity][w][k];
+      s[k] = t / D;
+    }
+    if (dx != nullptr) {
+#pragma unroll
+      for (int r = 0; r < kLnR; ++r) {
+        const int row = r0 + r;
+        if (row >= rows) break;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+          const int v = threadIdx.x + j * 256;
+          if (v >= nvec) continue;
+          float fx[8], fd[8], fa[8], o[8];
+          unpack8(ux[r][j], fx);
+          unpack8(ud[r][j], fd);
+          if (add != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(add + static_cast<long long>(row) * ldadd) + v), fa);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = (fx[i] - mu[r]) * rs[r];
+            o[i] = rs[r] * (fd[i] * gam[j][i] - s[2 * r] - xh * s[2 * r + 1]) + (add != nullptr ? fa[i] : 0.f);
+          }
+          reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx)[v] = pack8(o);
+        }
+      }
+    }
+  }
+  if (ws != nullptr) {
+    const long long chunks = gridDim.x;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int v = threadIdx.x + j * 256;
+      if (v >= nvec) continue;
+      float* wg = ws + (0 * chunks + blockIdx.x) * D + v * 8;
+      float* wb = ws + (1 * chunks + blockIdx.x) * D + v * 8;
+      *reinterpret_cast<float4*>(wg) = make_float4(pg[j][0], pg[j][1], pg[j][2], pg[j][3]);
+      *reinterpret_cast<float4*>(wg + 4) = make_float4(pg[j][4], pg[j][5], pg[j][6], pg[j][7]);
+      *reinterpret_cast<float4*>(wb) = make_float4(pb[j][0], pb[j][1], pb[j][2], pb[j][3]);
+      *reinterpret_cast<float4*>(wb + 4) = make_float4(pb[j][4], pb[j][5], pb[j][6], pb[j][7]);
+    }
+  }
+}
+
 __global__ void ln_bwd_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int D, int chunks, int accumulate) {
   pdl_launch_dependents();
@@ -169,6 +297,34 @@ __global__ void ln_bwd_finalize_kernel(const float* __restrict__ ws, float* __re
   }
   if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + g;
   if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + b;
+}
+
+// Wide finalize for the one-pass kernel's [2][chunks][D] partials (chunks up to one per SM): a CTA owns 32 columns,
+// its 8 thread rows stride over the chunks (coalesced 128 B reads), then a fixed-order smem reduction (deterministic).
+__global__ void __launch_bounds__(256)
+ln_bwd_finalize_wide_kernel(const float* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta, int D,
+                            int chunks, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float sg[8][32], sb[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float g = 0.f, b = 0.f;
+  if (c < D) {
+    for (int k = threadIdx.y; k < chunks; k += 8) {
+      g += ws[static_cast<long long>(k) * D + c];
+      b += ws[(static_cast<long long>(chunks) + k) * D + c];
+    }
+  }
+  sg[threadIdx.y][threadIdx.x] = g;
+  sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) { tg += sg[y][threadIdx.x]; tb += sb[y][threadIdx.x]; }
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + tg;
+    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + tb;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -209,6 +365,42 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
     if (i + 8 <= n) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(src + i)), b = __ldg(reinterpret_cast<const float4*>(src + i + 4));
       const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      *reinterpret_cast<uint4*>(dst + i) = pack8(f);
+    } else {
+      for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16(src[k]);
+    }
+  }
+}
+// Multi-tensor cast: one launch re-derives the bf16 copies of a whole list of fp32 tensors.  The device table holds one
+// {src, dst, n, first_block} record per tensor; block b finds its tensor by binary search over first_block and
+// converts elements [(b - first_block) * 4096, +4096) of it.
+struct CastSeg {
+  const float* src;
+  bf16* dst;
+  long long n;
+  long long blk0;
+};
+static_assert(sizeof(CastSeg) == 32, "table layout is part of the C ABI: 4 x int64 per tensor");
+constexpr int kCastSegElems = 4096;
+__global__ void __launch_bounds__(256) cast_multi_kernel(const CastSeg* __restrict__ segs, int nseg) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long b = blockIdx.x;
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&segs[mid].blk0) <= b) lo = mid; else hi = mid - 1;
+  }
+  const float* src = segs[lo].src;
+  bf16* dst = segs[lo].dst;
+  const long long n = segs[lo].n;
+  const long long base = (b - segs[lo].blk0) * kCastSegElems;
+#pragma unroll
+  for (int it = 0; it < kCastSegElems / (256 * 8); ++it) {
+    const long long i = base + (static_cast<long long>(it) * 256 + threadIdx.x) * 8;
+    if (i + 8 <= n) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + i)), c = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+      const float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
       *reinterpret_cast<uint4*>(dst + i) = pack8(f);
     } else {
       for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16(src[k]);
@@ -497,7 +689,21 @@ extern "C" int otb_layernorm_fwd(const void* x, int64_t ldx, const float* gamma,
   return OTB_OK;
 }
 
+static bool ln_fused_enabled() {
+  static const bool on = [] { const char* e = getenv("OTB_LN_FUSED"); return e && e[0] == '1'; }();
+  return on;
+}
+static int ln_fused_grid(int rows) {
+  const int nbatch = (rows + otb::kLnR - 1) / otb::kLnR;
+  return nbatch < otb::sm_count() ? nbatch : otb::sm_count();
+}
+
 extern "C" int otb_ln_chunks(int rows, int D) {
+  if (ln_fused_enabled() && D <= 4096) {        // workspace must hold one partial row per CTA of the one-pass kernel
+    const int g = ln_fused_grid(rows);
+    int colblocks0 = (D + 63) / 64, chunks0 = (4 * 148 + colblocks0 - 1) / colblocks0;
+    return g > chunks0 ? g : chunks0;
+  }
   int colblocks = (D + 63) / 64;
   int chunks = (4 * 148 + colblocks - 1) / colblocks;
   if (chunks > (rows + 7) / 8) chunks = (rows + 7) / 8;
@@ -511,6 +717,20 @@ extern "C" int otb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, in
                                  int D, void* stream) {
   OTB_CHECK_ARG(dy && x && mean && rstd && gamma && rows > 0 && D > 0, "otb_layernorm_bwd: bad argument");
   OTB_CHECK_ARG(D % 8 == 0 && lddy % 8 == 0 && ldx % 8 == 0, "otb_layernorm_bwd: D/ld must be multiples of 8");
+  if (ln_fused_enabled() && D <= 4096 && dx != nullptr && (dgamma != nullptr || dbeta != nullptr)) {
+    OTB_CHECK_ARG(lddx % 8 == 0 && (add == nullptr || ldadd % 8 == 0), "otb_layernorm_bwd: bad ld");
+    OTB_CHECK_ARG(ws != nullptr, "otb_layernorm_bwd: workspace required for parameter gradients");
+    const int grid = ln_fused_grid(rows);
+    auto kern = (D <= 2048) ? ln_bwd_fused_kernel<1> : ln_bwd_fused_kernel<2>;
+    OTB_CHECK_CUDA(launch_k(kern, dim3(grid), dim3(256), 0, ST(stream), static_cast<const bf16*>(dy), lddy,
+                            static_cast<const bf16*>(x), ldx, mean, rstd, gamma, static_cast<const bf16*>(add), ldadd,
+                            static_cast<bf16*>(dx), lddx, ws, rows, D));
+    OTB_CHECK_CUDA(launch_k(ln_bwd_finalize_wide_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, ST(stream), ws, dgamma,
+                            dbeta, D, grid, accumulate));
+    count_launch(2);
+    OTB_CHECK_CUDA(cudaGetLastError());
+    return OTB_OK;
+  }
   if (dx != nullptr) {
     OTB_CHECK_ARG(lddx % 8 == 0 && (add == nullptr || ldadd % 8 == 0), "otb_layernorm_bwd: bad ld");
     OTB_CHECK_CUDA(launch_k(ln_bwd_dx_kernel, dim3((rows + 7) / 8), dim3(256), 0, ST(stream), 
@@ -536,6 +756,16 @@ extern "C" int otb_text_time(const uint8_t* media_locations, int B, int L, int a
                              void* stream) {
   OTB_CHECK_ARG(media_locations && text_time && B > 0 && L > 0, "otb_text_time: bad argument");
   OTB_CHECK_CUDA(launch_k(text_time_kernel, dim3((B + 63) / 64), dim3(64), 0, ST(stream), media_locations, B, L, attend_previous, text_time));
+  count_launch();
+  OTB_CHECK_CUDA(cudaGetLastError());
+  return OTB_OK;
+}
+
+extern "C" int otb_cast_f32_bf16_multi(const void* table, int n_tensors, int64_t total_blocks, void* stream) {
+  OTB_CHECK_ARG(table && n_tensors > 0 && total_blocks > 0 && total_blocks < (1ll << 31),
+                "otb_cast_f32_bf16_multi: bad argument");
+  OTB_CHECK_CUDA(launch_k(cast_multi_kernel, dim3(static_cast<unsigned>(total_blocks)), dim3(256), 0, ST(stream),
+                          static_cast<const CastSeg*>(table), n_tensors));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;

@@ -33,7 +33,7 @@ int otb_compiled_arch(void);
 /* Number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
 long long otb_launch_count(void);
 /* sizeof() of the ABI structs as the C compiler laid them out: 0 otb_gemm_epilogue, 1 otb_attn_desc,
- * 2 otb_attn_grads (binding self-check for FFI hosts). */
+ * 2 otb_attn_grads, 3 otb_lm_attn_desc, 4 otb_lm_attn_grads (binding self-check for FFI hosts). */
 int otb_abi_sizeof(int which);
 
 /* ---------------------------------------------------------------------------------------------
@@ -122,6 +122,38 @@ int otb_attn_fwd(const otb_attn_desc* d, void* stream);
 int otb_attn_bwd(const otb_attn_desc* d, const otb_attn_grads* g, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SURVEY.md §8f rank 1 — causal self-attention of the frozen LM decoder layers (head_dim 128: MPT-7B / LLaMA-7B).
+ *   mpt/attention.py:22-84 (scaled_multihead_dot_product_attention), :457-464 (ALiBi key bias), :68-75 (causal mask)
+ * qkv is the fused Wqkv GEMM output [B*S][qkv_cols] bf16 (row pitch ld_qkv): head h of Q / K / V at columns
+ * q_col0 / k_col0 / v_col0 + h*128.  out [B*S][..] bf16, head h at out_col0 + h*128; lse fp32 [B][H][S].
+ *   score(i,j) = scale * q_i.k_j + alibi_slopes[h] * (j - (S-1))      (alibi_slopes NULL: no bias)
+ *   causal != 0: keys j > i are masked.
+ * Backward returns activation gradients only (the LM is frozen): dqkv has the layout of qkv.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct otb_lm_attn_desc {
+  const void* qkv;
+  void* out;
+  float* lse;
+  const float* alibi_slopes; /* fp32 [H] or NULL */
+  int64_t ld_qkv, ld_out;
+  int32_t qkv_cols, q_col0, k_col0, v_col0, out_col0;
+  int32_t B, H, S, head_dim, causal;
+  float scale;
+} otb_lm_attn_desc;
+
+typedef struct otb_lm_attn_grads {
+  const void* dout; /* [B*S][dout_cols] bf16, head h at dout_col0 + h*128 */
+  void* dqkv;       /* [B*S][..] bf16: dQ / dK / dV of head h at dq_col0 / dk_col0 / dv_col0 + h*128 */
+  float* dq_ws;     /* fp32 [B*S][H*128] scratch, required when S > 128 */
+  int64_t ld_dout, ld_dqkv;
+  int32_t dout_cols, dout_col0, dq_col0, dk_col0, dv_col0;
+  int32_t _pad;
+} otb_lm_attn_grads;
+
+int otb_lm_attn_fwd(const otb_lm_attn_desc* d, void* stream);
+int otb_lm_attn_bwd(const otb_lm_attn_desc* d, const otb_lm_attn_grads* g, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Index / mask construction (integer, bit-exact):  modeling_otter.py:296-311
  *   text_time[b,i] = cumsum(media_locations[b,:])[i]; if !attend_previous: +1 on non-media tokens,
  *   then entries > count_nonzero(media_locations[b]) wrap to 0.
@@ -149,6 +181,11 @@ int otb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, 
 /* dst(bf16)[i] = src(fp32)[i]  — bf16 shadow of fp32 master weights (autocast-equivalent). */
 int otb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int otb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+/* The same cast for a LIST of tensors in one launch (all trainable weights after an optimizer step).
+ * table: device array of n_tensors records {const float* src; bf16* dst; int64 n; int64 first_block}, 32 bytes each,
+ * sorted by first_block; tensor t owns blocks [first_block_t, first_block_t + ceil(n_t / 4096)); total_blocks is
+ * their sum.  src / dst must be 16-byte aligned. */
+int otb_cast_f32_bf16_multi(const void* table, int n_tensors, int64_t total_blocks, void* stream);
 /* out[r,:] = bf16(src[(r / div) % mod, :])  fp32 [mod][D] -> bf16 [rows][D]; latents repeat (:232). */
 int otb_bcast_rows(const float* src, int div, int mod, void* out, int rows, int D, void* stream);
 /* out[r,:] = x[r,:] + bias[(r / div) % mod, :]   bf16 [rows][D] + fp32 [mod][D]  (frame_embs add, :224-226) */

@@ -48,6 +48,26 @@ class AttnGrads(C.Structure):
     ]
 
 
+class LmAttnDesc(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p), ("out", C.c_void_p), ("lse", C.c_void_p), ("alibi_slopes", C.c_void_p),
+        ("ld_qkv", C.c_int64), ("ld_out", C.c_int64),
+        ("qkv_cols", C.c_int32), ("q_col0", C.c_int32), ("k_col0", C.c_int32), ("v_col0", C.c_int32),
+        ("out_col0", C.c_int32),
+        ("B", C.c_int32), ("H", C.c_int32), ("S", C.c_int32), ("head_dim", C.c_int32), ("causal", C.c_int32),
+        ("scale", C.c_float),
+    ]
+
+
+class LmAttnGrads(C.Structure):
+    _fields_ = [
+        ("dout", C.c_void_p), ("dqkv", C.c_void_p), ("dq_ws", C.c_void_p),
+        ("ld_dout", C.c_int64), ("ld_dqkv", C.c_int64),
+        ("dout_cols", C.c_int32), ("dout_col0", C.c_int32), ("dq_col0", C.c_int32), ("dk_col0", C.c_int32),
+        ("dv_col0", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/otter_b200.h declares
 _VP, _I, _I64, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
@@ -59,12 +79,15 @@ SIGNATURES = {
     "otb_gemm_bf16": (_I, [_VP, _I, _I64, _VP, _I, _I64, _I, _I, _I, C.POINTER(GemmEpilogue), _VP]),
     "otb_attn_fwd": (_I, [C.POINTER(AttnDesc), _VP]),
     "otb_attn_bwd": (_I, [C.POINTER(AttnDesc), C.POINTER(AttnGrads), _VP]),
+    "otb_lm_attn_fwd": (_I, [C.POINTER(LmAttnDesc), _VP]),
+    "otb_lm_attn_bwd": (_I, [C.POINTER(LmAttnDesc), C.POINTER(LmAttnGrads), _VP]),
     "otb_text_time": (_I, [_VP, _I, _I, _I, _VP, _VP]),
     "otb_layernorm_fwd": (_I, [_VP, _I64, _VP, _VP, _VP, _I64, _VP, _VP, _I, _I, _F, _VP]),
     "otb_ln_chunks": (_I, [_I, _I]),
     "otb_layernorm_bwd": (_I, [_VP, _I64, _VP, _I64, _VP, _VP, _VP, _VP, _I64, _VP, _I64, _VP, _VP, _I, _VP, _I, _I,
                                _VP]),
     "otb_cast_f32_bf16": (_I, [_VP, _VP, _I64, _VP]),
+    "otb_cast_f32_bf16_multi": (_I, [_VP, _I, _I64, _VP]),
     "otb_cast_bf16_f32": (_I, [_VP, _VP, _I64, _VP]),
     "otb_bcast_rows": (_I, [_VP, _I, _I, _VP, _I, _I, _VP]),
     "otb_add_rowbias": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP]),
@@ -102,7 +125,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    for i, st in enumerate((GemmEpilogue, AttnDesc, AttnGrads)):
+    for i, st in enumerate((GemmEpilogue, AttnDesc, AttnGrads, LmAttnDesc, LmAttnGrads)):
         if lib.otb_abi_sizeof(i) != C.sizeof(st):
             raise OtbError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes in ctypes, "
                            f"{lib.otb_abi_sizeof(i)} in the library")

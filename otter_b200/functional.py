@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import AttnDesc, AttnGrads, GemmEpilogue, check
+from ._lib import AttnDesc, AttnGrads, GemmEpilogue, LmAttnDesc, LmAttnGrads, check
 
 BF16 = torch.bfloat16
 
@@ -117,6 +117,50 @@ def linear_wgrad(dy, x, *, out=None, accumulate=False, **epi):
         out = torch.empty((N, K), device=dy.device, dtype=torch.float32)
         accumulate = False
     return _gemm_raw(dy, 1, dy.stride(0), x, 1, x.stride(0), N, K, M, out, accumulate=accumulate, **epi)
+
+
+# ------------------------------------------------------------------------------------------------
+# Causal self-attention of the frozen LM layers (head dim 128) — SURVEY.md §8f rank 1
+# ------------------------------------------------------------------------------------------------
+def _lm_desc(qkv, out, lse, slopes, B, S, H, causal, scale):
+    d = LmAttnDesc()
+    d.qkv, d.out, d.lse, d.alibi_slopes = _p(qkv), _p(out), _p(lse), _p(slopes)
+    d.ld_qkv, d.ld_out = qkv.stride(0), out.stride(0)
+    D = H * 128
+    d.qkv_cols, d.q_col0, d.k_col0, d.v_col0, d.out_col0 = qkv.shape[1], 0, D, 2 * D, 0
+    d.B, d.H, d.S, d.head_dim, d.causal = B, H, S, 128, 1 if causal else 0
+    d.scale = scale
+    return d
+
+
+def lm_attn_fwd(qkv, B, S, H, *, slopes=None, causal=True, scale=None):
+    """qkv bf16 [B*S, 3*H*128] (fused Wqkv output, [q|k|v]) -> (out bf16 [B*S, H*128], lse fp32 [B, H, S])."""
+    qkv = _mat(qkv, "qkv")
+    assert qkv.shape == (B * S, 3 * H * 128), qkv.shape
+    if slopes is not None:
+        _req(slopes, torch.float32, "alibi slopes")
+    out = torch.empty((B * S, H * 128), device=qkv.device, dtype=BF16)
+    lse = torch.empty((B, H, S), device=qkv.device, dtype=torch.float32)
+    scale = (128 ** -0.5) if scale is None else scale
+    d = _lm_desc(qkv, out, lse, slopes, B, S, H, causal, scale)
+    check(_lib.load().otb_lm_attn_fwd(C.byref(d), _stream()), "otb_lm_attn_fwd")
+    return out, lse
+
+
+def lm_attn_bwd(dout, qkv, out, lse, B, S, H, *, slopes=None, causal=True, scale=None):
+    """-> dqkv bf16 [B*S, 3*H*128] ([dq|dk|dv], the layout of qkv)."""
+    dout, qkv, out = _mat(dout, "dout"), _mat(qkv, "qkv"), _mat(out, "out")
+    scale = (128 ** -0.5) if scale is None else scale
+    d = _lm_desc(qkv, out, lse, slopes, B, S, H, causal, scale)
+    dqkv = torch.empty_like(qkv)
+    g = LmAttnGrads()
+    ws = torch.empty((B * S, H * 128), device=qkv.device, dtype=torch.float32) if S > 128 else None
+    D = H * 128
+    g.dout, g.dqkv, g.dq_ws = _p(dout), _p(dqkv), _p(ws)
+    g.ld_dout, g.ld_dqkv = dout.stride(0), dqkv.stride(0)
+    g.dout_cols, g.dout_col0, g.dq_col0, g.dk_col0, g.dv_col0 = dout.shape[1], 0, 0, D, 2 * D
+    check(_lib.load().otb_lm_attn_bwd(C.byref(d), C.byref(g), _stream()), "otb_lm_attn_bwd")
+    return dqkv
 
 
 # ------------------------------------------------------------------------------------------------
@@ -244,6 +288,15 @@ def cast_bf16(src, out=None):
         out = torch.empty(src.shape, device=src.device, dtype=BF16)
     check(_lib.load().otb_cast_f32_bf16(_p(src), _p(out), src.numel(), _stream()), "otb_cast_f32_bf16")
     return out
+
+
+CAST_MULTI_BLOCK = 4096      # elements per block of otb_cast_f32_bf16_multi (kCastSegElems)
+
+
+def cast_bf16_multi(table, n_tensors, total_blocks):
+    """table: int64 [n_tensors, 4] on the device = {src ptr, dst ptr, numel, first block} per tensor."""
+    assert table.dtype == torch.int64 and table.is_contiguous() and table.shape == (n_tensors, 4)
+    check(_lib.load().otb_cast_f32_bf16_multi(_p(table), n_tensors, total_blocks, _stream()), "otb_cast_f32_bf16_multi")
 
 
 def cast_f32(src, out=None):

@@ -82,9 +82,49 @@ def invalidate(params):
             _shadow[id(p)] = (-1, hit[1], hit[2], hit[3])
 
 
+# (id, data_ptr, shadow ptr) of every member -> (device table, total blocks): the table of one refresh() call
+_tables = {}
+
+
+def refresh(params):
+    """Re-derive the bf16 shadows of all fp32 `params` in ONE multi-tensor launch (what `invalidate` + lazy
+    `bf16_of` do in one launch per weight).  The pointer table is built on first use — outside any CUDA-graph
+    capture — and reused while the parameters and their shadow buffers stay where they are."""
+    todo = []
+    for p in params:
+        t = p.detach()
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or t.data_ptr() % 16:
+            continue                                    # bf16_of() handles these one by one
+        hit = _shadow.get(id(p))
+        if hit is not None and hit[3]() is not p:
+            hit = None
+        out = hit[2] if (hit is not None and hit[2].shape == t.shape and hit[2].device == t.device) else \
+            torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+        todo.append((p, t, out))
+    if not todo:
+        return
+    key = tuple((id(p), t.data_ptr(), out.data_ptr()) for p, t, out in todo)
+    ent = _tables.get(key)
+    if ent is None:
+        rows, blk = [], 0
+        for p, t, out in todo:
+            rows.append([t.data_ptr(), out.data_ptr(), t.numel(), blk])
+            blk += (t.numel() + F.CAST_MULTI_BLOCK - 1) // F.CAST_MULTI_BLOCK
+        if len(_tables) > 8:
+            _tables.clear()
+        ent = (torch.tensor(rows, dtype=torch.int64, device=todo[0][1].device), blk)
+        _tables[key] = ent
+    F.cast_bf16_multi(ent[0], len(todo), ent[1])
+    for p, t, out in todo:
+        hit = _shadow.get(id(p))
+        ref = hit[3] if (hit is not None and hit[3]() is p) else _ref(_shadow, p)
+        _shadow[id(p)] = (p._version, t.data_ptr(), out, ref)
+
+
 def clear_caches():
     _shadow.clear()
     _f32.clear()
+    _tables.clear()
 
 
 class GradSink:

@@ -67,7 +67,7 @@ def test_gemm_layouts_and_epilogues():
     assert_close(y2, big[:, 256:512].float() @ w.float().t(), BF_RTOL, BF_ATOL, "strided A")
 
 
-@pytest.mark.parametrize("rows,D", [(37, 256), (512, 1024), (300, 4096)])
+@pytest.mark.parametrize("rows,D", [(37, 256), (512, 1024), (300, 4096), (101, 3072), (2, 2048)])
 def test_layernorm_fwd_bwd(rows, D):
     from otter_b200 import functional as F
     x = rnd(rows, D, scale=2.0)
@@ -269,3 +269,22 @@ def test_label_mask_bit_exact_and_shifted_cross_entropy():
     loss = losses.shifted_cross_entropy(x, torch.full((1, 4), -100, device=dev()))
     loss.backward()
     assert loss.item() == 0.0 and x.grad.abs().max().item() == 0.0
+
+
+def test_multi_tensor_cast_matches_per_tensor_cast():
+    """params.refresh(): one launch for a list of fp32 weights == torch round-to-nearest-even bf16, bit for bit."""
+    from otter_b200 import params as P
+    torch.manual_seed(5)
+    shapes = [(1,), (7,), (4096,), (4097,), (33, 129), (1024, 1024), (3, 5, 7), (2048, 4096)]
+    ps = [torch.nn.Parameter(torch.randn(*s, device=dev()) * 3) for s in shapes]
+    P.refresh(ps)
+    for p in ps:
+        got = P.bf16_of(p)
+        assert got.shape == p.shape
+        assert torch.equal(got, p.detach().to(torch.bfloat16)), p.shape
+    with torch.no_grad():
+        for p in ps:
+            p.mul_(1.5)                                  # version bump: shadows stale
+    P.refresh(ps)                                        # second call reuses the pointer table and the shadow buffers
+    for p in ps:
+        assert torch.equal(P.bf16_of(p), p.detach().to(torch.bfloat16)), p.shape
