@@ -793,13 +793,8 @@ extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
   if (d->Sk2 > 0) rc = make_tmap_bf16_2d(&mk2, d->kv2, (uint64_t)d->P * d->Sk2, d->kv2_cols, d->ldkv2, 128, 64);
   else mk2 = mk1;
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwdSmem));
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (1 + 2 * 3 + 4) * kTileBytes + 1024 + 2048));
-    attr = true;
-  }
+  OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_kernel, kAttnFwdSmem));
+  OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_resident_kernel, (1 + 2 * 3 + 4) * kTileBytes + 1024 + 2048));
   dim3 grid((d->Sq + 127) / 128, d->H, d->P);
   const int nt = (d->Sk1 + 127) / 128 + (d->Sk2 + 127) / 128;
   if (nt <= 3) {
@@ -839,11 +834,7 @@ extern "C" int otb_attn_bwd(const otb_attn_desc* d, const otb_attn_grads* g, voi
   if (d->Sk2 > 0) rc = make_tmap_bf16_2d(&mk2, d->kv2, (uint64_t)d->P * d->Sk2, d->kv2_cols, d->ldkv2, 128, 64);
   else mk2 = mk1;
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
-    attr = true;
-  }
+  OTB_CHECK_CUDA(ensure_dyn_smem(attn_bwd_kernel, kAttnBwdSmem));
   dim3 grid(d->H, d->P);
   OTB_CHECK_CUDA(launch_k(attn_bwd_kernel, dim3(grid), dim3(kAttnThreads), kAttnBwdSmem, static_cast<cudaStream_t>(stream), mq, mdo, mk1, mk2, p));
   count_launch();

@@ -526,11 +526,7 @@ extern "C" int otb_lm_attn_fwd(const otb_lm_attn_desc* d, void* stream) {
   CUtensorMap mqkv;
   rc = make_tmap_bf16_2d(&mqkv, d->qkv, (uint64_t)d->B * d->S, d->qkv_cols, d->ld_qkv, 128, 64);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(lm_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmFwdSmem));
-    attr = true;
-  }
+  OTB_CHECK_CUDA(ensure_dyn_smem(lm_attn_fwd_kernel, kLmFwdSmem));
   dim3 grid((d->S + 127) / 128, d->H, d->B);
   OTB_CHECK_CUDA(launch_k(lm_attn_fwd_kernel, grid, dim3(kLmThreads), kLmFwdSmem, static_cast<cudaStream_t>(stream), mqkv, p));
   count_launch();
@@ -555,11 +551,7 @@ extern "C" int otb_lm_attn_bwd(const otb_lm_attn_desc* d, const otb_lm_attn_grad
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&mdo, g->dout, (uint64_t)d->B * d->S, g->dout_cols, g->ld_dout, 128, 64);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(lm_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLmBwdSmem));
-    attr = true;
-  }
+  OTB_CHECK_CUDA(ensure_dyn_smem(lm_attn_bwd_kernel, kLmBwdSmem));
   dim3 grid(d->H, d->B);
   OTB_CHECK_CUDA(launch_k(lm_attn_bwd_kernel, grid, dim3(kLmThreads), kLmBwdSmem, static_cast<cudaStream_t>(stream), mqkv, mdo, p));
   count_launch();

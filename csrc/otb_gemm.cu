@@ -456,11 +456,7 @@ static int launch_gemm(const void* A, long long lda, const void* B, long long ld
   }
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, MC, TS>;
   constexpr int smem_bytes = Cfg::kSmemBytes + (TS ? kEpiStageBytes : 0);
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  OTB_CHECK_CUDA(ensure_dyn_smem(kern, smem_bytes));   // per (instantiation, device)
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + BN - 1) / BN;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[2];
@@ -656,11 +652,7 @@ static int launch_gemm2(const void* A, long long lda, const void* B, long long l
   }
   auto kern = gemm2_bf16_kernel<A_MN, B_MN, TS>;
   constexpr int smem_bytes = k2SmemBytes + (TS ? kEpiStageBytes : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  OTB_CHECK_CUDA(ensure_dyn_smem(kern, smem_bytes));
   const int num_pt = ((M + 255) / 256) * ((N + 255) / 256);
   const int max_clusters = sm_count() / 2;
   cudaLaunchConfig_t cfg = {};

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 
 namespace otb {
 
@@ -39,46 +40,80 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows, uint32_t box_cols) {
+// ---- descriptor cache --------------------------------------------------------------------------------------
+// A CUtensorMap is a pure function of (base, rows, cols, pitch, box, element type): identical keys always encode to
+// identical 128 bytes, so a hit can never be stale.  The cache removes the driver call (~1 us each, 2-4 per launch)
+// from eager-mode launches (generate(), the tests); it is guarded by a mutex because serving calls generate() from
+// worker threads (SURVEY.md 8b threading row) and bounded so that long-running processes cannot grow it.
+namespace {
+struct TmapKey {
+  uintptr_t base; uint64_t rows, cols, ld; uint32_t box_rows, box_cols, elt;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && elt == o.elt;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = k.base * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.ld + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= ((uint64_t(k.box_rows) << 34) | (uint64_t(k.box_cols) << 2) | k.elt) + (h << 6) + (h >> 2);
+    return static_cast<size_t>(h);
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+constexpr size_t kTmapCacheMax = 8192;
+std::atomic<long long> g_tmap_hits{0}, g_tmap_misses{0};
+}  // namespace
+
+static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                        uint32_t box_rows, uint32_t box_cols, bool f32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(OTB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const uint32_t esz = f32 ? 4 : 2;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(OTB_ERR_INVALID, "TMA base not 16B aligned");
-  if ((ld * 2) % 16 != 0) return set_error(OTB_ERR_INVALID, "TMA row pitch %llu elements not a multiple of 8",
-                                            (unsigned long long)ld);
-  if (box_cols * 2 != 128 || box_rows > 256) return set_error(OTB_ERR_INVALID, "bad TMA box");
+  if ((ld * esz) % 16 != 0)
+    return set_error(OTB_ERR_INVALID, "TMA row pitch %llu elements not a multiple of 16 bytes", (unsigned long long)ld);
+  if (box_cols * esz != 128 || box_rows > 256) return set_error(OTB_ERR_INVALID, "bad TMA box");
+  const TmapKey key{reinterpret_cast<uintptr_t>(base), rows, cols, ld, box_rows, box_cols, esz};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *map = it->second;
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return OTB_OK;
+    }
+  }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * esz};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return set_error(OTB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
-                     (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+    return set_error(OTB_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u",
+                     f32 ? "f32" : "bf16", (int)r, (unsigned long long)rows, (unsigned long long)cols,
+                     (unsigned long long)ld, box_rows, box_cols);
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() >= kTmapCacheMax) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *map);
   return OTB_OK;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(map, base, rows, cols, ld, box_rows, box_cols, false);
 }
 
 int make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return set_error(OTB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(OTB_ERR_INVALID, "TMA base not 16B aligned");
-  if ((ld * 4) % 16 != 0) return set_error(OTB_ERR_INVALID, "TMA row pitch %llu fp32 elements not a multiple of 4",
-                                            (unsigned long long)ld);
-  if (box_cols * 4 != 128 || box_rows > 256) return set_error(OTB_ERR_INVALID, "bad TMA box");
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 4};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return set_error(OTB_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
-                     (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
-  return OTB_OK;
+  return make_tmap_2d(map, base, rows, cols, ld, box_rows, box_cols, true);
 }
 
 bool pdl_enabled() {
@@ -86,14 +121,36 @@ bool pdl_enabled() {
   return on;
 }
 
+// Per-device state.  Function attributes and the SM count belong to a DEVICE, not to the process: the reference's
+// demos place the model with device_map="auto" (pipeline/demos/demo_models.py:37), so one process may launch on several
+// GPUs, and from several threads.
+constexpr int kMaxDevices = 64;
+
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+cudaError_t ensure_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, uint64_t> done;     // func -> bit mask of devices already configured
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  std::lock_guard<std::mutex> lk(mu);
+  uint64_t& mask = done[func];
+  if (mask & (1ull << dev)) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) mask |= (1ull << dev);
+  return e;
 }
 
 }  // namespace otb
@@ -103,6 +160,7 @@ const char* otb_last_error(void) { return otb::g_err; }
 int otb_version(void) { return 1; }
 int otb_compiled_arch(void) { return 100; }
 long long otb_launch_count(void) { return otb::g_launches.load(); }
+long long otb_tmap_cache_stat(int which) { return which ? otb::g_tmap_misses.load() : otb::g_tmap_hits.load(); }
 int otb_abi_sizeof(int which) {
   switch (which) {
     case 0: return (int)sizeof(otb_gemm_epilogue);

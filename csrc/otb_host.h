@@ -34,7 +34,11 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 int make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols);
 
-int sm_count();
+int sm_count();   // of the CURRENT device (cached per device)
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (kernel, device); thread-safe
+cudaError_t ensure_dyn_smem(const void* func, int bytes);
+template <typename F>
+inline cudaError_t ensure_dyn_smem(F* kern, int bytes) { return ensure_dyn_smem(reinterpret_cast<const void*>(kern), bytes); }
 bool pdl_enabled();   // OTB_PDL=1 enables programmatic dependent launch (measured neutral under graph replay; off by default)
 
 // Launch with the programmatic-stream-serialization attribute (all otter_b200 kernels call pdl_wait()).

@@ -214,11 +214,7 @@ extern "C" int otb_label_mask(const int64_t* input_ids, int B, int L, int64_t eo
   OTB_CHECK_ARG(input_ids && labels && B > 0 && L > 0, "otb_label_mask: bad argument");
   const size_t lm_smem = static_cast<size_t>(L) * 16;
   OTB_CHECK_ARG(lm_smem <= 200 * 1024, "otb_label_mask: L too long for the shared-memory staging (max 12800)");
-  static bool lm_attr = false;
-  if (!lm_attr) {
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(label_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    lm_attr = true;
-  }
+  OTB_CHECK_CUDA(ensure_dyn_smem(label_mask_kernel, 200 * 1024));
   OTB_CHECK_CUDA(launch_k(label_mask_kernel, dim3(B), dim3(128), lm_smem, ST(stream),
                           reinterpret_cast<const long long*>(input_ids), B, L, (long long)eos_id, (long long)answer_id,
                           (long long)eoc_id, (long long)mask_val, reinterpret_cast<long long*>(labels)));
@@ -239,12 +235,8 @@ extern "C" int otb_shifted_cross_entropy(const void* logits, int logits_fp32, in
   const size_t row_bytes = static_cast<size_t>(V) * (logits_fp32 ? 4 : 2);
   const bool in_smem = row_bytes <= 200 * 1024;
   const size_t ce_smem = in_smem ? ((row_bytes + 15) & ~size_t(15)) : 0;
-  static bool ce_attr = false;
-  if (!ce_attr) {
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(ce_row_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
-    OTB_CHECK_CUDA(cudaFuncSetAttribute(ce_row_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
-    ce_attr = true;
-  }
+  OTB_CHECK_CUDA(ensure_dyn_smem(ce_row_kernel<float, true>, 200 * 1024 + 16));
+  OTB_CHECK_CUDA(ensure_dyn_smem(ce_row_kernel<bf16, true>, 200 * 1024 + 16));
 #define OTB_CE_LAUNCH(T_, S_)                                                                                       \
   OTB_CHECK_CUDA(launch_k(ce_row_kernel<T_, S_>, dim3((unsigned)rows), dim3(512), ce_smem, ST(stream),              \
                           static_cast<const T_*>(logits), (long long)ld, lab, L, V, (const float*)count, row_loss,  \

@@ -659,8 +659,10 @@ __global__ void fuyu_scatter_kernel(const bf16* __restrict__ word, const bf16* _
     const long long tok = i / nvec;
     const int b = static_cast<int>(tok / S);
     const long long id = idx[tok];
-    const uint4* src = (id >= 0) ? reinterpret_cast<const uint4*>(cont + (b_off[b] + id) * D)
-                                 : reinterpret_cast<const uint4*>(word + tok * D);
+    // b_off holds B+1 prefix offsets: ids outside sample b's [0, n_b) keep the word row instead of reading out of bounds
+    const bool take = id >= 0 && id < b_off[b + 1] - b_off[b];
+    const uint4* src = take ? reinterpret_cast<const uint4*>(cont + (b_off[b] + id) * D)
+                            : reinterpret_cast<const uint4*>(word + tok * D);
     reinterpret_cast<uint4*>(out + tok * D)[v] = __ldg(src + v);
   }
 }

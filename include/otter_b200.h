@@ -32,6 +32,9 @@ int otb_version(void);
 int otb_compiled_arch(void);
 /* Number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
 long long otb_launch_count(void);
+/* TMA descriptor cache statistics (which = 0: hits, 1: misses).  Descriptors are cached by (base, shape, pitch, box)
+ * under a mutex (SURVEY.md 8b "no global mutable state beyond a mutex-guarded descriptor cache"). */
+long long otb_tmap_cache_stat(int which);
 /* sizeof() of the ABI structs as the C compiler laid them out: 0 otb_gemm_epilogue, 1 otb_attn_desc,
  * 2 otb_attn_grads, 3 otb_lm_attn_desc, 4 otb_lm_attn_grads (binding self-check for FFI hosts). */
 int otb_abi_sizeof(int which);
@@ -230,8 +233,10 @@ int otb_clip_assemble(const void* patch_emb, const float* cls, const float* pos,
 /* media[img*v + t, :] = hidden[img, 1+t, :] (+ frame_embs[img % F])  (modeling_otter.py:991,224-227) */
 int otb_media_from_clip(const void* hidden, const float* frame_embs, int F, void* out, int n_img, int v, int D,
                         void* stream);
-/* Fuyu patch scatter (fuyu/modeling_fuyu.py:65-77): for s with idx[b,s] >= 0:
- * out[b,s,:] = cont[b_off[b] + idx[b,s], :] ; else out[b,s,:] = word[b,s,:]. bf16, D % 8 == 0. */
+/* Fuyu patch scatter (fuyu/modeling_fuyu.py:65-77): for s with 0 <= idx[b,s] < n_b:
+ * out[b,s,:] = cont[b_off[b] + idx[b,s], :] ; else out[b,s,:] = word[b,s,:]. bf16, D % 8 == 0.
+ * b_off: int64 [B+1] prefix offsets of the samples' rows inside `cont` (n_b = b_off[b+1] - b_off[b]); ids >= n_b never
+ * read out of bounds (the host wrapper raises the reference's ValueError for them before launching). */
 int otb_fuyu_scatter(const void* word, const void* cont, const int64_t* idx, const int64_t* b_off, void* out,
                      int B, int S, int D, void* stream);
 

@@ -17,10 +17,21 @@ import sys
 import types
 
 REF_ROOT = os.environ.get("OTTER_REFERENCE_ROOT", "/root/reference")
+# the same package packed by oracle/build_ref.py (git-ignored artefact that travels to the GPU box)
+REF_ZIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "otter_ai_ref.zip")
+
+
+def reference_tree_available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "src/otter_ai/models/otter/modeling_otter.py"))
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "src/otter_ai/models/otter/modeling_otter.py"))
+    """The reference's python package can be imported: from /root/reference, or from oracle/_ref's archive."""
+    return reference_tree_available() or os.path.isfile(REF_ZIP)
+
+
+def reference_origin() -> str:
+    return REF_ROOT if reference_tree_available() else (REF_ZIP if os.path.isfile(REF_ZIP) else "")
 
 
 class FakeTokenizer:
@@ -96,7 +107,8 @@ def load_reference_otter():
     if not reference_available():
         raise RuntimeError(f"reference not found under {REF_ROOT}")
     _install_stubs()
-    for p in (os.path.join(REF_ROOT, "src"), REF_ROOT):
+    paths = (os.path.join(REF_ROOT, "src"), REF_ROOT) if reference_tree_available() else (REF_ZIP + "/src",)
+    for p in paths:
         if p not in sys.path:
             sys.path.insert(0, p)
     mod = importlib.import_module("otter_ai.models.otter.modeling_otter")

@@ -75,6 +75,7 @@ SIGNATURES = {
     "otb_version": (_I, []),
     "otb_compiled_arch": (_I, []),
     "otb_launch_count": (C.c_longlong, []),
+    "otb_tmap_cache_stat": (C.c_longlong, [_I]),
     "otb_abi_sizeof": (_I, [_I]),
     "otb_gemm_bf16": (_I, [_VP, _I, _I64, _VP, _I, _I64, _I, _I, _I, C.POINTER(GemmEpilogue), _VP]),
     "otb_attn_fwd": (_I, [C.POINTER(AttnDesc), _VP]),

@@ -184,6 +184,9 @@ class MediaFromClipFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, hidden, frame_embs, F_frames):
+        if frame_embs is not None and F_frames > frame_embs.shape[0]:
+            raise ValueError(f"{F_frames} frames per media but frame_embs holds max_num_frames={frame_embs.shape[0]} "
+                             "(modeling_otter.py:224-226)")
         ctx.fe, ctx.cfg = frame_embs, (F_frames, hidden.shape[1] - 1, hidden.shape[2])
         fe = f32_of(frame_embs) if frame_embs is not None else None
         return F.media_from_clip(hidden, fe, F_frames)
@@ -345,6 +348,9 @@ def clip_vision_forward(pixel_values, W):
     N = pixel_values.shape[0]
     patch, D, heads = W["patch"], W["D"], W["heads"]
     np_ = (pixel_values.shape[2] // patch) * (pixel_values.shape[3] // patch)
+    if np_ + 1 != W["pos"].shape[0]:          # the kernels index the position table unchecked (HF raises the same way)
+        raise ValueError(f"Input image size ({pixel_values.shape[2]}*{pixel_values.shape[3]}) doesn't match model "
+                         f"({W['pos'].shape[0] - 1} patches of {patch}*{patch}).")
     cols = F.im2col_patches(pixel_values, patch, W["Kpad"])                               # clip.py:74 conv as GEMM
     pe = F.linear_fwd(cols, W["patch_w"])
     h = F.clip_assemble(pe, W["cls"], W["pos"], N, np_)                                   # clip.py:77-80

@@ -48,10 +48,12 @@ class FlatGradBuffer:
         self.comm = None
         if comm_dtype is not None and comm_dtype != dtype:
             self.comm = self._alloc(off, comm_dtype, device)
+        self.views = []
         for p, o in zip(self.params, self.offsets):
             view = self.flat[o:o + p.numel()].view(p.shape)
             if p.dtype != dtype:
                 raise TypeError(f"FlatGradBuffer({dtype}) needs {dtype} parameters (fp32 master weights); got {p.dtype}")
+            self.views.append(view)
             p.grad = view
             if dtype == torch.float32:
                 p._otb_grad = view          # sink used by otter_b200 backward kernels
@@ -77,18 +79,33 @@ class FlatGradBuffer:
         """Start a step.  Parameters whose gradients are written by otter_b200 kernels (`_otb_sink_user`, learned
         on first use) are only marked empty — the first kernel write overwrites, later ones accumulate, so the
         multi-GB buffer needs no zero-fill pass.  Parameters that receive gradients through plain autograd
-        accumulation (e.g. LM embeddings) are zeroed here, like optimizer.zero_grad()."""
-        for p in self.params:
+        accumulation (e.g. LM embeddings) are zeroed here, like optimizer.zero_grad().
+
+        `optimizer.zero_grad()` (set_to_none=True is the default, and what the reference's loop calls:
+        pipeline/train/instruction_following.py:213) detaches `.grad` from the flat buffer; every view is re-attached
+        here, so begin_step() is the only reset a train loop needs and the kernels' sinks, `.grad` and the buffer the
+        all-reduce sends stay one and the same memory."""
+        for p, view in zip(self.params, self.views):
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
             if getattr(p, "_otb_sink_user", False):
                 p._otb_grad_live = False
-            elif p.grad is not None:
-                p.grad.zero_()
+            else:
+                view.zero_()
 
     def finish_step(self):
-        """Kernel-written sinks nobody touched this step (unused parameters) must read as zero before the reduce."""
-        for p in self.params:
-            if getattr(p, "_otb_sink_user", False) and not p._otb_grad_live:
-                p._otb_grad.zero_()
+        """Kernel-written sinks nobody touched this step (unused parameters) must read as zero before the reduce.
+        Also repairs the aliasing if `optimizer.zero_grad()` ran AFTER begin_step(): a gradient autograd then
+        accumulated outside the buffer is copied in, and every `.grad` is a view of the buffer again."""
+        for p, view in zip(self.params, self.views):
+            sink = getattr(p, "_otb_sink_user", False)
+            if sink and not p._otb_grad_live:
+                view.zero_()
+            g = p.grad
+            if g is None or g.data_ptr() != view.data_ptr():
+                if g is not None and not sink:
+                    view.copy_(g)
+                p.grad = view
 
     def all_reduce(self, group=None, async_op=False):
         """The one collective of the step: mean over ranks (DDP semantics)."""

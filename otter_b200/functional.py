@@ -5,6 +5,7 @@ operation on the hot path is a kernel of libotter_b200.so.  All activations are 
 unit column stride (row pitch may exceed the logical width so column slices work in place).
 """
 import ctypes as C
+import functools
 
 import torch
 
@@ -16,6 +17,35 @@ BF16 = torch.bfloat16
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _device_of(args, kwargs):
+    """Device index shared by every tensor argument (OtbError if they disagree); None if there is no tensor."""
+    dev = None
+    for a in (*args, *kwargs.values()):
+        if isinstance(a, AttnSpec):
+            a = a.q
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            i = a.device.index
+            if dev is None:
+                dev = i
+            elif i != dev:
+                raise _lib.OtbError(f"tensors live on different devices (cuda:{dev} and cuda:{i})")
+    return dev
+
+
+def _on_device(fn):
+    """The C library launches on the CURRENT device and stream.  The reference places models with
+    device_map="auto" (pipeline/demos/demo_models.py:37), so an op may be called with tensors of a non-current GPU:
+    switch to the tensors' device for the duration of the call (the stream is then that device's current stream)."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _device_of(args, kwargs)
+        if dev is None or dev == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 def _p(t):
@@ -83,6 +113,7 @@ def _gemm_raw(A, a_mn, lda, B, b_mn, ldb, M, N, K, out, *, bias=None, act=0, aux
     return out
 
 
+@_on_device
 def linear_fwd(x, w, *, out=None, out_dtype=BF16, **epi):
     """y[M,N] = epilogue(x[M,K] @ w[N,K]^T)   (nn.Linear forward)."""
     x, w = _mat(x, "x"), _mat(w, "w")
@@ -96,6 +127,7 @@ def linear_fwd(x, w, *, out=None, out_dtype=BF16, **epi):
     return _gemm_raw(x, 0, x.stride(0), w, 0, w.stride(0), M, N, K, out, **epi)
 
 
+@_on_device
 def linear_dgrad(dy, w, *, out=None, out_dtype=BF16, **epi):
     """dx[M,K] = epilogue(dy[M,N] @ w[N,K])   — w is consumed MN-major in place (no transpose copy)."""
     dy, w = _mat(dy, "dy"), _mat(w, "w")
@@ -107,6 +139,7 @@ def linear_dgrad(dy, w, *, out=None, out_dtype=BF16, **epi):
     return _gemm_raw(dy, 0, dy.stride(0), w, 1, w.stride(0), M, K, N, out, **epi)
 
 
+@_on_device
 def linear_wgrad(dy, x, *, out=None, accumulate=False, **epi):
     """dW[N,K] (fp32) (+)= dy[M,N]^T @ x[M,K]   — both operands consumed MN-major in place."""
     dy, x = _mat(dy, "dy"), _mat(x, "x")
@@ -133,6 +166,7 @@ def _lm_desc(qkv, out, lse, slopes, B, S, H, causal, scale):
     return d
 
 
+@_on_device
 def lm_attn_fwd(qkv, B, S, H, *, slopes=None, causal=True, scale=None):
     """qkv bf16 [B*S, 3*H*128] (fused Wqkv output, [q|k|v]) -> (out bf16 [B*S, H*128], lse fp32 [B, H, S])."""
     qkv = _mat(qkv, "qkv")
@@ -147,6 +181,7 @@ def lm_attn_fwd(qkv, B, S, H, *, slopes=None, causal=True, scale=None):
     return out, lse
 
 
+@_on_device
 def lm_attn_bwd(dout, qkv, out, lse, B, S, H, *, slopes=None, causal=True, scale=None):
     """-> dqkv bf16 [B*S, 3*H*128] ([dq|dk|dv], the layout of qkv)."""
     dout, qkv, out = _mat(dout, "dout"), _mat(qkv, "qkv"), _mat(out, "out")
@@ -166,6 +201,7 @@ def lm_attn_bwd(dout, qkv, out, lse, B, S, H, *, slopes=None, causal=True, scale
 # ------------------------------------------------------------------------------------------------
 # LayerNorm
 # ------------------------------------------------------------------------------------------------
+@_on_device
 def layernorm_fwd(x, gamma, beta, eps=1e-5, want_stats=True, out=None):
     x2 = _mat(x, "x")
     _req(gamma, torch.float32, "gamma"), _req(beta, torch.float32, "beta")
@@ -179,6 +215,7 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, want_stats=True, out=None):
     return (y if out is not None else y.view(x.shape)), mean, rstd
 
 
+@_on_device
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, add=None, want_dx=True, dgamma=None, dbeta=None, accumulate=False,
                   want_param_grads=True):
     """Returns (dx or None, dgamma, dbeta). `add` (bf16, same shape) is summed into dx (fused residual grad)."""
@@ -239,6 +276,7 @@ class AttnSpec:
         return d
 
 
+@_on_device
 def attn_fwd(spec, out=None, out_col0=0, want_lse=True):
     if out is None:
         out = torch.empty((spec.P * spec.Sq, spec.H * 64), device=spec.q.device, dtype=BF16)
@@ -248,6 +286,7 @@ def attn_fwd(spec, out=None, out_col0=0, want_lse=True):
     return out, lse
 
 
+@_on_device
 def attn_bwd(spec, out, out_col0, lse, dout, dout_col0, dq, dq_col0, dkv1, dk1_col0, dv1_col0, dkv2=None, dk2_col0=0,
              dv2_col0=0):
     d = spec.desc(out, out_col0, lse)
@@ -265,6 +304,7 @@ def attn_bwd(spec, out, out_col0, lse, dout, dout_col0, dq, dq_col0, dkv1, dk1_c
     return dq, dkv1, dkv2
 
 
+@_on_device
 def text_time(media_locations, attend_previous=True):
     """bool/uint8 [B,L] -> int32 [B,L]  (bit-exact restatement of modeling_otter.py:298-311)."""
     ml = media_locations
@@ -281,6 +321,7 @@ def text_time(media_locations, attend_previous=True):
 # ------------------------------------------------------------------------------------------------
 # small passes
 # ------------------------------------------------------------------------------------------------
+@_on_device
 def cast_bf16(src, out=None):
     _req(src, torch.float32, "src")
     src = src.contiguous()
@@ -293,12 +334,14 @@ def cast_bf16(src, out=None):
 CAST_MULTI_BLOCK = 4096      # elements per block of otb_cast_f32_bf16_multi (kCastSegElems)
 
 
+@_on_device
 def cast_bf16_multi(table, n_tensors, total_blocks):
     """table: int64 [n_tensors, 4] on the device = {src ptr, dst ptr, numel, first block} per tensor."""
     assert table.dtype == torch.int64 and table.is_contiguous() and table.shape == (n_tensors, 4)
     check(_lib.load().otb_cast_f32_bf16_multi(_p(table), n_tensors, total_blocks, _stream()), "otb_cast_f32_bf16_multi")
 
 
+@_on_device
 def cast_f32(src, out=None):
     _req(src, BF16, "src")
     src = src.contiguous()
@@ -308,6 +351,7 @@ def cast_f32(src, out=None):
     return out
 
 
+@_on_device
 def bcast_rows(src, rows, div, mod):
     _req(src, torch.float32, "src")
     D = src.shape[-1]
@@ -316,6 +360,7 @@ def bcast_rows(src, rows, div, mod):
     return out
 
 
+@_on_device
 def add_rowbias(x, bias, div, mod):
     x2 = _mat(x, "x")
     assert x2.is_contiguous()
@@ -326,6 +371,7 @@ def add_rowbias(x, bias, div, mod):
     return out
 
 
+@_on_device
 def grouped_colsum(x, div, mod, out=None, accumulate=False):
     x2 = _mat(x, "x")
     rows, D = x2.shape
@@ -337,6 +383,7 @@ def grouped_colsum(x, div, mod, out=None, accumulate=False):
     return out
 
 
+@_on_device
 def gate_grad(dy, a, gate, dgate=None, accumulate=False):
     lib = _lib.load()
     _req(dy, BF16, "dy"), _req(a, BF16, "a"), _req(gate, torch.float32, "gate")
@@ -350,6 +397,7 @@ def gate_grad(dy, a, gate, dgate=None, accumulate=False):
     return dgate
 
 
+@_on_device
 def sqmean_loss(x, want_grad=True):
     lib = _lib.load()
     _req(x, BF16, "x")
@@ -361,6 +409,7 @@ def sqmean_loss(x, want_grad=True):
     return loss, dx
 
 
+@_on_device
 def im2col_patches(pixels, patch, Kpad):
     assert pixels.is_cuda and pixels.dim() == 4 and pixels.shape[1] == 3
     pixels = pixels.contiguous()
@@ -373,6 +422,7 @@ def im2col_patches(pixels, patch, Kpad):
     return out
 
 
+@_on_device
 def clip_assemble(patch_emb, cls, pos, N, np_):
     D = patch_emb.shape[-1]
     out = torch.empty((N, np_ + 1, D), device=patch_emb.device, dtype=BF16)
@@ -381,6 +431,7 @@ def clip_assemble(patch_emb, cls, pos, N, np_):
     return out
 
 
+@_on_device
 def media_from_clip(hidden, frame_embs, F):
     """hidden bf16 [n_img, 1+v, D] -> bf16 [n_img*v, D] (CLS dropped, + frame_embs[img % F] if given)."""
     _req(hidden, BF16, "hidden")
@@ -391,9 +442,13 @@ def media_from_clip(hidden, frame_embs, F):
     return out
 
 
+@_on_device
 def fuyu_scatter(word, cont, idx, b_off):
+    """b_off: int64 [B+1] prefix offsets of each sample's rows in `cont` (see otb_fuyu_scatter)."""
     _req(word, BF16, "word"), _req(cont, BF16, "cont")
     B, S, D = word.shape
+    if b_off.numel() != B + 1 or b_off.dtype != torch.int64 or idx.dtype != torch.int64:
+        raise _lib.OtbError("fuyu_scatter: b_off must be int64 [B+1] and idx int64 [B,S]")
     out = torch.empty_like(word)
     check(_lib.load().otb_fuyu_scatter(_p(word.contiguous()), _p(cont.contiguous()), _p(idx.contiguous()),
                                        _p(b_off.contiguous()), _p(out), B, S, D, _stream()), "otb_fuyu_scatter")
@@ -406,6 +461,7 @@ def fuyu_scatter(word, cont, idx, b_off):
 F32_KCHUNK = 512
 
 
+@_on_device
 def epilogue_f32(acc, *, bias=None, act=0, scale_ptr=None, scale_tanh=False, residual=None):
     """fp32 epilogue of the chunked fp32-grade GEMM: act(acc + bias) * gate + residual (otb_epilogue_f32)."""
     acc = _mat(acc, "acc", torch.float32)
@@ -416,6 +472,7 @@ def epilogue_f32(acc, *, bias=None, act=0, scale_ptr=None, scale_tanh=False, res
     return out
 
 
+@_on_device
 def split3_concat(src, pattern):
     """fp32 [rows, K] -> bf16 [rows, 6K]: three-term bf16 split laid out for the 6-product GEMM."""
     src = _mat(src, "src", torch.float32)
@@ -425,6 +482,7 @@ def split3_concat(src, pattern):
     return out
 
 
+@_on_device
 def linear_f32(x, w6, N, *, bias=None, act=0, scale_ptr=None, scale_tanh=False, residual=None):
     """y fp32 [M,N] = epilogue(x fp32 [M,K] @ W^T) with fp32-grade accuracy; w6 = split3_concat(W, 1)."""
     x = _mat(x, "x", torch.float32)
@@ -451,6 +509,7 @@ def linear_f32(x, w6, N, *, bias=None, act=0, scale_ptr=None, scale_tanh=False, 
     return out
 
 
+@_on_device
 def layernorm_fwd_f32(x, gamma, beta, eps=1e-5):
     x2 = _mat(x, "x", torch.float32)
     rows, D = x2.shape
@@ -461,6 +520,7 @@ def layernorm_fwd_f32(x, gamma, beta, eps=1e-5):
     return y.view(x.shape)
 
 
+@_on_device
 def add_rowbias_f32(x, bias, div, mod):
     x2 = _mat(x, "x", torch.float32)
     assert x2.is_contiguous()
@@ -471,6 +531,7 @@ def add_rowbias_f32(x, bias, div, mod):
     return out
 
 
+@_on_device
 def attn_fwd_f32(spec):
     """spec: AttnSpec(dtype=torch.float32) -> fp32 [P*Sq, H*64]."""
     out = torch.empty((spec.P * spec.Sq, spec.H * 64), device=spec.q.device, dtype=torch.float32)

@@ -11,9 +11,10 @@ import torch
 
 from . import _lib
 from ._lib import check
-from .functional import _p, _stream
+from .functional import _on_device, _p, _stream
 
 
+@_on_device
 def label_mask(input_ids, eos_token_id, answer_token_id, endofchunk_token_id, masking_number=-100):
     """int64 [B, L] -> int64 labels [B, L] exactly as the reference's masking()."""
     if not input_ids.is_cuda or input_ids.dtype != torch.int64:
@@ -28,6 +29,7 @@ def label_mask(input_ids, eos_token_id, answer_token_id, endofchunk_token_id, ma
 
 class _ShiftedCE(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, logits, labels):
         lib = _lib.load()
         B, L, V = logits.shape
@@ -45,6 +47,7 @@ class _ShiftedCE(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_on_device
     def backward(ctx, grad_out):
         d = ctx.dlogits
         if d is None:

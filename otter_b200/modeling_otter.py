@@ -39,6 +39,9 @@ class _AddRowBiasFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bias, div, mod):
         from .params import f32_of
+        if mod > bias.shape[0]:       # the kernel indexes bias[(row // div) % mod] unchecked
+            raise ValueError(f"{mod} frames / media per sample but the embedding table holds {bias.shape[0]} rows "
+                             "(max_num_frames / max_num_media, modeling_otter.py:224-229)")
         ctx.bias, ctx.cfg = bias, (div, mod)
         return F.add_rowbias(x, f32_of(bias)[:mod].contiguous(), div, mod)
 

@@ -23,13 +23,18 @@ def test_reference_arm_nonzero_rank_is_silent():
 
 
 def test_reference_arm_json_line(tmp_path):
-    """One bounded step of the CPU port (batch 1 of the c2 workload; ~7 s on 8 cores)."""
+    """One bounded step of the CPU arm (batch 1 of the c2 workload here to keep the CPU suite short; the driver's run
+    uses the GPU arm's batch 8): the reference's own modules when /root/reference or oracle/_ref is present."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, timeout=900)
+                          "--warmup", "0", "--ref-batch", "1"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
     assert d["metric"] == "samples/sec perceiver+gated-xattn fwd+bwd" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shims
+    want_kind = "reference" if ref_shims.reference_available() else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["per_gpu_batch"] == 1 and d["cpu_baseline"]["batch"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["steps"] == 1

@@ -84,3 +84,40 @@ def test_shard_batch_partitions_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_zero_grad_set_to_none_keeps_the_flat_buffer_live():
+    """The reference's loop calls optimizer.zero_grad() (set_to_none=True by default) every step
+    (pipeline/train/instruction_following.py:213): `.grad` must be a view of the flat buffer again after
+    begin_step(), in either call order, and a kernel-sink parameter whose `.grad` was dropped must still be seen
+    by the optimizer."""
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    flat = FlatGradBuffer(lin.parameters(), device="cpu")
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    sink = lin[1].weight                                   # pretend an otter_b200 wgrad epilogue writes this one
+    X = torch.randn(4, 6)
+    for order in ("zero_then_begin", "begin_then_zero", "zero_then_begin"):
+        if order == "zero_then_begin":
+            opt.zero_grad()
+            flat.begin_step()
+        else:
+            flat.begin_step()
+            opt.zero_grad()
+        assert order == "begin_then_zero" or all(p.grad is not None for p in flat.params)
+        before = [p.detach().clone() for p in lin.parameters()]
+        # the "kernel" path: gradient written straight into the sink view, autograd gets None for it
+        sink.requires_grad_(False)
+        lin(X).pow(2).mean().backward()
+        sink.requires_grad_(True)
+        sink._otb_grad.fill_(0.25)
+        sink._otb_grad_live = True
+        sink._otb_sink_user = True
+        flat.finish_step()
+        for p, v in zip(flat.params, flat.views):
+            assert p.grad is not None and p.grad.data_ptr() == v.data_ptr()
+        assert flat.flat.abs().sum() > 0
+        opt.step()
+        for p, b in zip(lin.parameters(), before):
+            assert not torch.equal(p.detach(), b), "optimizer skipped a parameter"
+        assert torch.allclose(sink.detach(), before[2] - 0.1 * 0.25)

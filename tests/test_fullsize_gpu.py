@@ -85,7 +85,7 @@ def test_c5_fuyu_patch_linear_and_scatter():
     pp = torch.zeros(n_p, Kp, dtype=torch.bfloat16); pp[:, :K] = patches
     wp = torch.zeros(D, Kp, dtype=torch.bfloat16); wp[:, :K] = w
     emb = F.linear_fwd(pp.to(DEV), wp.to(DEV), bias=bias.to(DEV))
-    out = F.fuyu_scatter(word.to(DEV), emb, idx.to(DEV), torch.zeros(1, dtype=torch.int64, device=DEV))
+    out = F.fuyu_scatter(word.to(DEV), emb, idx.to(DEV), torch.tensor([0, n_p], dtype=torch.int64, device=DEV))
     ref = R.fuyu_patch_embed([patches.float()], w.float(), bias, word.float(), idx, q=R.bf16_round)
     err = (out.float().cpu() - ref).abs()
     assert err.max().item() <= 2e-2 + 1e-2 * ref.abs().max().item()
@@ -150,3 +150,35 @@ def test_resampler_odd_shapes_vs_oracle(b, T, Fr, v, n_lat):
         out32 = rs(x)
     err = (out32.float().cpu() - ref.detach()).abs()
     assert (err > 1e-5 + 1e-3 * ref.detach().abs()).sum().item() == 0, err.max().item()
+
+
+@torch.no_grad()
+def test_c5_fuyu_module_entry_reference_signature_and_errors():
+    """otter_b200.modeling_fuyu with the reference's argument names, shapes (K = 2700, no caller-side padding) and
+    errors (modeling_fuyu.py:61-62,73-76), two samples with different patch counts, against the oracle."""
+    from otter_b200 import modeling_fuyu as MF
+    g = torch.Generator().manual_seed(2)
+    K, D, S = 2700, 4096, 700
+    lin = torch.nn.Linear(K, D).to(DEV)
+    emb_tok = torch.nn.Embedding(100, D).to(DEV).to(torch.bfloat16)
+    counts = [300, 525]
+    patches = [torch.randn(1, n, K, generator=g).to(torch.bfloat16).to(DEV) for n in counts]
+    ids = torch.randint(0, 100, (2, S), generator=g).to(DEV)
+    idx = torch.full((2, S), -1, dtype=torch.int64)
+    idx[0, 10:10 + 300] = torch.arange(300)
+    idx[1, 3:3 + 525] = torch.arange(525)
+    out = MF.embed_inputs(emb_tok, lin, ids, image_patches=patches, image_patches_indices=idx.to(DEV))
+    w = lin.weight.detach().to(torch.bfloat16).float().cpu()
+    ref = R.fuyu_patch_embed([p_[0].float().cpu() for p_ in patches], w, lin.bias.detach().float().cpu(),
+                             emb_tok(ids).float().cpu(), idx, q=R.bf16_round)
+    err = (out.float().cpu() - ref).abs()
+    assert err.max().item() <= 2e-2 + 1e-2 * ref.abs().max().item()
+    # cached decode step: patches ignored (modeling_fuyu.py:124)
+    o2 = MF.embed_inputs(emb_tok, lin, ids, image_patches=patches, image_patches_indices=idx.to(DEV), past_key_values=((),))
+    assert torch.equal(o2, emb_tok(ids))
+    word = emb_tok(ids)
+    with pytest.raises(ValueError, match="Batch sizes must match"):
+        MF.gather_continuous_embeddings(word, [torch.zeros(3, D, device=DEV)], idx.to(DEV))
+    with pytest.raises(ValueError, match="does not match number of continuous token ids"):
+        MF.gather_continuous_embeddings(word, [torch.zeros(299, D, device=DEV, dtype=torch.bfloat16),
+                                               torch.zeros(525, D, device=DEV, dtype=torch.bfloat16)], idx.to(DEV))

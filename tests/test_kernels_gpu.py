@@ -234,8 +234,11 @@ def test_small_passes():
     idx[0, 2:5] = torch.arange(3)
     idx[1, 1:5] = torch.tensor([3, 2, 1, 0])
     ref = fuyu_gather_continuous_embeddings(word.cpu().float(), [c.cpu().float() for c in cont], idx)
-    got = F.fuyu_scatter(word, torch.cat(cont), idx.to(dev()), torch.tensor([0, 3], device=dev()))
+    got = F.fuyu_scatter(word, torch.cat(cont), idx.to(dev()), torch.tensor([0, 3, 7], device=dev()))
     assert torch.equal(got.cpu().float(), ref)
+    idx[1, 9] = 4                                   # id == n_1: out of range -> never read out of bounds, word row kept
+    got = F.fuyu_scatter(word, torch.cat(cont), idx.to(dev()), torch.tensor([0, 3, 7], device=dev()))
+    assert torch.equal(got[1, 9], word[1, 9])
 
 
 def test_label_mask_bit_exact_and_shifted_cross_entropy():
