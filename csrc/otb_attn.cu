@@ -21,6 +21,8 @@
 //   tt == 0        -> attention row zeroed after softmax (output row exactly 0, no gradients)
 //   1 <= tt <= T   -> only keys of media slot tt-1 participate
 //   tt > T         -> every key masked with -FLT_MAX => uniform attention 1/(T*n); dS = 0, dV gets dO/(T*n)
+#include <cstdlib>
+
 #include "otb_common.cuh"
 #include "otb_host.h"
 
@@ -502,6 +504,280 @@ attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 }
 
 // ================================================================================================
+// forward, warp-specialised resident variant (<= 3 key tiles): the default for CLIP (S = 257), the perceiver on
+// image features (320 keys) and the gated cross-attention (64 * T keys).
+//
+//   warp 0      TMA producer: Q tiles (double-buffered), then every K / V tile once — they stay resident in smem
+//               for all query tiles of this (problem, head), so CLIP reads K/V once instead of once per query tile
+//   warp 1      allocates TMEM; one lane issues every tcgen05.mma:  S_j = Q K_j^T  (N = the tile's key count
+//               rounded up to 16, so a 1-key remainder tile costs one 16-wide MMA instead of a 128-wide one) and
+//               O += P_j V_j (double-buffered O so the next query tile's S overlaps this tile's epilogue)
+//   warps 2-9   softmax + epilogue: warp pair (w, w+4) shares TMEM lane quarter w % 4 (= rows) and splits each key
+//               tile's 16-column chunks even / odd; row max and row sum are exchanged inside the pair through smem
+//               and a 64-thread named barrier.  P tiles (bf16, SW128) are double-buffered.
+// Every hand-off is an mbarrier (TMA complete_tx, tcgen05.commit, or one arrive per softmax warp): there is no
+// __syncthreads between the prologue and the teardown.
+// ================================================================================================
+constexpr int kWsThreads = 320;
+__global__ void __launch_bounds__(kWsThreads, 1)
+attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv1,
+                   const __grid_constant__ CUtensorMap map_kv2, AttnParams p, int nt, int nq_per_cta, int tmem_cols) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;                              // 2 x 16 KB
+  uint8_t* s_k = s_q + 2 * kTileBytes;              // nt x 16 KB
+  uint8_t* s_v = s_k + nt * kTileBytes;             // nt x 16 KB
+  uint8_t* s_p = s_v + nt * kTileBytes;             // 2 x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 4 * kTileBytes);
+  uint64_t* bar_q = bars;             // [2] Q tile landed
+  uint64_t* bar_qfree = bars + 2;     // [2] S MMAs that read the Q buffer retired
+  uint64_t* full_k = bars + 4;        // [3]
+  uint64_t* full_v = bars + 7;        // [3]
+  uint64_t* bar_s = bars + 10;        // [3] S_j complete (once per query tile)
+  uint64_t* bar_sfree = bars + 13;    //     softmax finished reading S of this query tile (8 warp arrivals)
+  uint64_t* p_ready = bars + 14;      // [2] P buffer written (8 warp arrivals)
+  uint64_t* bar_pv = bars + 16;       // [2] P V MMA that read the P buffer retired
+  uint64_t* bar_o = bars + 18;        // [2] O buffer complete
+  uint64_t* bar_ofree = bars + 20;    // [2] epilogue finished reading the O buffer (8 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  __shared__ float red_m[256];        // [2 column halves][128 rows]
+  __shared__ float red_l[256];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.y, prob = blockIdx.z;
+  const int nqt = (p.Sq + 127) / 128;
+  const int qt0 = blockIdx.x * nq_per_cta;
+  const int nq = min(nq_per_cta, nqt - qt0);
+  const int nt1 = (p.Sk1 + 127) / 128;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_q[i], 1); mbar_init(&bar_qfree[i], 1); mbar_init(&p_ready[i], 8); mbar_init(&bar_pv[i], 1);
+      mbar_init(&bar_o[i], 1); mbar_init(&bar_ofree[i], 8);
+    }
+    for (int i = 0; i < 3; ++i) { mbar_init(&full_k[i], 1); mbar_init(&full_v[i], 1); mbar_init(&bar_s[i], 1); }
+    mbar_init(bar_sfree, 8);
+    fence_mbar_init();
+    // the loads need no TMEM: start them before the CTA-wide prologue barrier
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_kv1); tma_prefetch_desc(&map_kv2);
+    pdl_wait();   // predecessor grid complete before any global / TMA access
+    mbar_arrive_expect_tx(&bar_q[0], kTileBytes);
+    tma_load_2d(s_q, &map_q, &bar_q[0], p.q_col0 + h * 64, prob * p.Sq + qt0 * 128);
+    for (int j = 0; j < nt; ++j) {
+      const KeyTile kt = key_tile(p, prob, j, nt1);
+      const CUtensorMap* m = kt.src ? &map_kv2 : &map_kv1;
+      mbar_arrive_expect_tx(&full_k[j], kTileBytes);
+      tma_load_2d(s_k + j * kTileBytes, m, &full_k[j], (kt.src ? p.k2_col0 : p.k1_col0) + h * 64, kt.row0);
+    }
+    for (int j = 0; j < nt; ++j) {
+      const KeyTile kt = key_tile(p, prob, j, nt1);
+      const CUtensorMap* m = kt.src ? &map_kv2 : &map_kv1;
+      mbar_arrive_expect_tx(&full_v[j], kTileBytes);
+      tma_load_2d(s_v + j * kTileBytes, m, &full_v[j], (kt.src ? p.v2_col0 : p.v1_col0) + h * 64, kt.row0);
+    }
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_o = tmem + nt * 128;       // two 64-column O buffers
+
+  if (warp == 0) {
+    // ===================== TMA producer: the remaining Q tiles =====================
+    if (lane == 0) {
+      for (int it = 1; it < nq; ++it) {
+        const int qb = it & 1;
+        if (it >= 2) mbar_wait(&bar_qfree[qb], ((it >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&bar_q[qb], kTileBytes);
+        tma_load_2d(s_q + qb * kTileBytes, &map_q, &bar_q[qb], p.q_col0 + h * 64, prob * p.Sq + (qt0 + it) * 128);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+      for (int it = 0; it < nq; ++it) {
+        const int qb = it & 1, ob = it & 1;
+        mbar_wait(&bar_q[qb], (it >> 1) & 1);
+        if (it > 0) mbar_wait(bar_sfree, (it - 1) & 1);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc(smem_u32(s_q + qb * kTileBytes), 16, 1024);
+        for (int j = 0; j < nt; ++j) {
+          if (it == 0) { mbar_wait(&full_k[j], 0); tc_fence_after(); }
+          const KeyTile kt = key_tile(p, prob, j, nt1);
+          const int ncols = (kt.valid + 15) & ~15;
+          const uint32_t idesc_s = make_idesc_bf16(128, ncols, false, false);
+          const uint64_t db = make_smem_desc(smem_u32(s_k + j * kTileBytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + j * 128, da + k * 2, db + k * 2, idesc_s, k != 0);
+          umma_commit(&bar_s[j]);
+        }
+        umma_commit(&bar_qfree[qb]);
+        if (it >= 2) { mbar_wait(&bar_ofree[ob], ((it >> 1) - 1) & 1); tc_fence_after(); }
+        for (int j = 0; j < nt; ++j) {
+          const int g = it * nt + j, b = g & 1;
+          const KeyTile kt = key_tile(p, prob, j, nt1);
+          const int ksteps = (kt.valid + 15) >> 4;
+          mbar_wait(&p_ready[b], (g >> 1) & 1);
+          if (it == 0) mbar_wait(&full_v[j], 0);
+          tc_fence_after();
+          const uint8_t* pbuf = s_p + b * 2 * kTileBytes;
+          const uint64_t db = make_smem_desc(smem_u32(s_v + j * kTileBytes), 16, 1024);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t dp = make_smem_desc(smem_u32(pbuf + (k >> 2) * kTileBytes) + (k & 3) * 32, 16, 1024);
+            umma_bf16(t_o + ob * 64, dp, db + k * 128, idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&bar_pv[b]);
+        }
+        umma_commit(&bar_o[ob]);
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue warps =====================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // even / odd 16-column chunks
+    const int r_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    pdl_wait();
+    for (int it = 0; it < nq; ++it) {
+      const int qt = qt0 + it, ob = it & 1;
+      const int row = qt * 128 + r_in_tile;
+      const bool row_ok = row < p.Sq;
+      const bool warp_active = (qt * 128 + quarter * 32) < p.Sq;      // warp-uniform
+      int tt = 0;
+      if (p.text_time != nullptr && row_ok) tt = p.text_time[prob * p.Sq + row];
+      const int cls = row_ok ? row_class(p, tt) : 0;
+
+      // ---- sweep 1: row max over the resident S tiles ----
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      for (int j = 0; j < nt; ++j) {
+        mbar_wait(&bar_s[j], it & 1);
+        if (!warp_active) continue;
+        tc_fence_after();
+        const KeyTile kt = key_tile(p, prob, j, nt1);
+        const RowRange rr = row_range(p, cls, tt, kt);
+        const int nch = (kt.valid + 15) >> 4;
+        for (int c = half; c < nch; c += 2) {
+          uint32_t r[16];
+          tmem_ld16(tmem + lane_addr + j * 128 + c * 16, r);
+          tmem_ld_wait();
+          if (cls == 1) {
+            const int c0 = c * 16;
+            if (c0 >= rr.lo && c0 + 16 <= rr.hi) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i >= rr.lo && c0 + i < rr.hi) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+            }
+          }
+        }
+      }
+      float m_run = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      if (warp_active) {
+        red_m[half * 128 + r_in_tile] = m_run;
+        named_bar_sync(1 + quarter, 64);
+        m_run = fmaxf(m_run, red_m[(half ^ 1) * 128 + r_in_tile]);
+      }
+
+      // ---- sweep 2: P = exp2((S - m) * scale * log2 e) -> smem (bf16), row sums ----
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      const float mb = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
+      for (int j = 0; j < nt; ++j) {
+        const int g = it * nt + j, b = g & 1;
+        if (g >= 2) mbar_wait(&bar_pv[b], ((g >> 1) - 1) & 1);       // the P V MMA that read this buffer retired
+        if (warp_active) {
+          const KeyTile kt = key_tile(p, prob, j, nt1);
+          const RowRange rr = row_range(p, cls, tt, kt);
+          const int nch = (kt.valid + 15) >> 4;
+          uint8_t* pbuf = s_p + b * 2 * kTileBytes;
+          for (int c = half; c < nch; c += 2) {
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_addr + j * 128 + c * 16, r);
+            tmem_ld_wait();
+            float pv[16];
+            const int c0 = c * 16;
+            if (cls == 1 && c0 >= rr.lo && c0 + 16 <= rr.hi) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+                ls[i & 3] += pv[i];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float v = 0.f;
+                if (c0 + i >= rr.lo && c0 + i < rr.hi)
+                  v = (cls == 1) ? ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb)) : 1.0f;
+                pv[i] = v;
+                ls[i & 3] += v;
+              }
+            }
+            uint8_t* chunk = pbuf + (c >> 2) * kTileBytes;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              uint4 o;
+              o.x = pack_bf16x2(pv[u * 8 + 0], pv[u * 8 + 1]); o.y = pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]);
+              o.z = pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]); o.w = pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]);
+              st_sw128(chunk, r_in_tile, (c & 3) * 16 + u * 8, o);
+            }
+          }
+          fence_proxy_async_smem();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[b]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree);                          // S may be overwritten by the next query tile
+
+      float l_run = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      if (warp_active) {
+        red_l[half * 128 + r_in_tile] = l_run;
+        named_bar_sync(1 + quarter, 64);
+        l_run += red_l[(half ^ 1) * 128 + r_in_tile];
+      }
+      // ---- epilogue: O / l -> bf16 (this warp: 32 of the 64 head columns), LSE ----
+      mbar_wait(&bar_o[ob], (it >> 1) & 1);
+      tc_fence_after();
+      if (warp_active) {
+        const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+        uint32_t r[32];
+        tmem_ld32(t_o + ob * 64 + lane_addr + half * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          bf16* dst = p.out + static_cast<long long>(prob * p.Sq + row) * p.ldo + p.o_col0 + h * 64 + half * 32;
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[g4 * 8 + 0]) * inv_l, __uint_as_float(r[g4 * 8 + 1]) * inv_l);
+            o.y = pack_bf16x2(__uint_as_float(r[g4 * 8 + 2]) * inv_l, __uint_as_float(r[g4 * 8 + 3]) * inv_l);
+            o.z = pack_bf16x2(__uint_as_float(r[g4 * 8 + 4]) * inv_l, __uint_as_float(r[g4 * 8 + 5]) * inv_l);
+            o.w = pack_bf16x2(__uint_as_float(r[g4 * 8 + 6]) * inv_l, __uint_as_float(r[g4 * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + g4 * 8) = o;
+          }
+          if (half == 0 && p.lse != nullptr)
+            p.lse[(static_cast<long long>(prob) * p.H + h) * p.Sq + row] =
+                (cls == 1 && l_run > 0.f) ? (m_run * p.scale + logf(l_run)) : 0.f;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ofree[ob]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, tmem_cols);
+  }
+}
+
+// ================================================================================================
 // backward
 // ================================================================================================
 __global__ void __launch_bounds__(kAttnThreads)
@@ -795,9 +1071,22 @@ extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
   if (rc) return rc;
   OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_kernel, kAttnFwdSmem));
   OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_resident_kernel, (1 + 2 * 3 + 4) * kTileBytes + 1024 + 2048));
+  OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_ws_kernel, (2 + 2 * 3 + 4) * kTileBytes + 1024 + 512));
   dim3 grid((d->Sq + 127) / 128, d->H, d->P);
   const int nt = (d->Sk1 + 127) / 128 + (d->Sk2 + 127) / 128;
-  if (nt <= 3) {
+  // OTB_ATTN_WS=0 selects the round-1 resident kernel (kept for A/B measurements)
+  static const bool ws_on = [] { const char* v = getenv("OTB_ATTN_WS"); return !(v && v[0] == '0'); }();
+  if (nt <= 3 && ws_on) {
+    // one CTA keeps K/V resident for ALL query tiles of its (problem, head) when that already fills the chip
+    // (CLIP: 8 images x 16 heads = 128 CTAs, one wave); otherwise one query tile per CTA for more parallelism
+    const int nqt = (d->Sq + 127) / 128;
+    const int nq_per_cta = (d->P * d->H >= (sm_count() * 4) / 5) ? nqt : 1;
+    const int smem = (2 + 2 * nt + 4) * kTileBytes + 1024 + 512;
+    const int tmem_cols = (nt == 1) ? 256 : 512;            // nt x 128 (S) + 2 x 64 (O)
+    dim3 g((nqt + nq_per_cta - 1) / nq_per_cta, d->H, d->P);
+    OTB_CHECK_CUDA(launch_k(attn_fwd_ws_kernel, g, dim3(kWsThreads), smem, static_cast<cudaStream_t>(stream), mq, mk1,
+                            mk2, p, nt, nq_per_cta, tmem_cols));
+  } else if (nt <= 3) {
     const int smem = (1 + 2 * nt + 4) * kTileBytes + 1024 + 2048;
     const int tmem_cols = (nt == 1) ? 256 : 512;
     OTB_CHECK_CUDA(launch_k(attn_fwd_resident_kernel, dim3(grid), dim3(kResThreads), smem, static_cast<cudaStream_t>(stream), mq, mk1, mk2, p, nt,

@@ -121,7 +121,9 @@ def _heads(t, P, S, H):
 
 
 @pytest.mark.parametrize("P,H,Sq,Sk1,Sk2", [(2, 8, 64, 256, 64), (1, 2, 64, 96, 64), (3, 4, 257, 257, 0),
-                                             (2, 2, 64, 2048, 64), (2, 8, 300, 64, 0)])
+                                             (2, 2, 64, 2048, 64), (2, 8, 300, 64, 0),
+                                             # >= 119 (problem, head) pairs: one CTA walks ALL query tiles with K/V resident
+                                             (8, 16, 257, 257, 0), (16, 8, 300, 64, 0), (15, 8, 700, 130, 64)])
 def test_attention_fwd_bwd_unmasked(P, H, Sq, Sk1, Sk2):
     from otter_b200 import functional as F
     inner = H * 64

@@ -19,6 +19,10 @@ run() {  # name, env assignments..., -- command
   tail -n 3 "$out/$name.log"
 }
 
+# the new warp-specialised attention forward (default on) is validated separately at the end: sections 1-6 run the
+# round-1 resident kernel so that a bug in the new kernel cannot take the other validations down
+export OTB_ATTN_WS=0
+
 # 1. new parity tests first (the round-1 verdict's hole), then the default full suite
 TMO=600 run pytest_c2_parity -- python -m pytest tests/test_c2_parity_gpu.py -m gpu -x -q
 TMO=900 run pytest_default_full -- python -m pytest tests -m gpu -q --deselect tests/test_lm_gpu.py
@@ -56,4 +60,15 @@ TMO=400 run bench_reference_arm -- python bench.py --impl reference --steps 3 --
 # 6. baseline profiles of the attention kernels at the step's shapes (ncu --set full) and the step's launch list
 TMO=400 run ncu_attn -- ncu --set full --clock-control none --import-source on -k regex:attn -s 9 -c 3 -o "$out/r02_attn_base" python tools/prof_attn.py
 TMO=600 run ncu_launches -- ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 700 --csv --log-file "$out/r02_launches_base.csv" python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline --no-extras --no-self-check --no-kernel-rooflines
+
+# 7. the warp-specialised attention forward: kernel + module parity, micro-timings, step-level A/B
+export OTB_ATTN_WS=1
+run ws_pytest_kernels -- python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "attn or attention"
+run ws_pytest_modules -- python -m pytest tests/test_modules_gpu.py tests/test_fullsize_gpu.py tests/test_c2_parity_gpu.py -m gpu -q
+run ws_prof_attn -- python tools/prof_attn.py
+OTB_ATTN_WS=0 run old_prof_attn -- python tools/prof_attn.py
+run ws_bench -- $B
+OTB_ATTN_WS=0 run old_bench -- $B
+run ws_bench_all OTB_GEMM_EPI_TMA=1 OTB_LN_FUSED=1 OTB_GEMM2_MIN_PAIRS=32 -- $B --multi-cast
+TMO=400 run ws_ncu_attn -- ncu --set full --clock-control none --import-source on -k regex:attn_fwd_ws -s 9 -c 3 -o "$out/r02_attn_ws" python tools/prof_attn.py
 echo done
