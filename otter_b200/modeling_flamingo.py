@@ -15,7 +15,7 @@ class FlamingoPerceiverBlock(OtterPerceiverBlock):
 
 
 class FlamingoPerceiverResampler(OtterPerceiverResampler):
-    pass
+    _block_cls = FlamingoPerceiverBlock
 
 
 class FlamingoMaskedCrossAttention(OtterMaskedCrossAttention):
@@ -23,7 +23,7 @@ class FlamingoMaskedCrossAttention(OtterMaskedCrossAttention):
 
 
 class FlamingoGatedCrossAttentionBlock(OtterGatedCrossAttentionBlock):
-    pass
+    _attn_cls = FlamingoMaskedCrossAttention
 
 
 class FlamingoLayer(OtterLayer):
@@ -31,11 +31,28 @@ class FlamingoLayer(OtterLayer):
 
 
 class FlamingoLMMixin(OtterLMMixin):
-    pass
+    """modeling_flamingo.py:399-474 — `init_flamingo` is the reference's name for the same wiring."""
+    _layer_cls = FlamingoLayer
+    _gated_cls = FlamingoGatedCrossAttentionBlock
+
+    def init_flamingo(self, media_token_id, vis_hidden_size, cross_attn_every_n_layers,
+                      use_media_placement_augmentation):
+        return self.init_otter(media_token_id=media_token_id, vis_hidden_size=vis_hidden_size,
+                               cross_attn_every_n_layers=cross_attn_every_n_layers,
+                               use_media_placement_augmentation=use_media_placement_augmentation)
 
 
 class FlamingoConfig(OtterConfig):
+    """configuration_flamingo.py — same fields as OtterConfig under model_type "flamingo"."""
     model_type = "flamingo"
+
+    def __init__(self, vision_config=None, text_config=None, cross_attn_every_n_layers: int = 4,
+                 use_media_placement_augmentation: bool = True, **kwargs):
+        # explicit: transformers 5.x synthesises an __init__ for config subclasses that do not define one, which would
+        # skip OtterConfig's dispatch of text_config / vision_config into config objects
+        super().__init__(vision_config=vision_config, text_config=text_config,
+                         cross_attn_every_n_layers=cross_attn_every_n_layers,
+                         use_media_placement_augmentation=use_media_placement_augmentation, **kwargs)
 
 
 class _FlamingoBase(_OtterBase):
@@ -46,6 +63,7 @@ class _FlamingoBase(_OtterBase):
     _honour_media_placement_augmentation = True
     _use_frame_embs = False
     _perceiver_cls = FlamingoPerceiverResampler
+    _lm_mixin_cls = FlamingoLMMixin
 
 
 class FlamingoPreTrainedModel(_FlamingoBase):

@@ -98,6 +98,7 @@ class OtterPerceiverBlock(nn.Module):
 
 class OtterPerceiverResampler(nn.Module):
     """reference :187-235."""
+    _block_cls = None          # Flamingo twin: FlamingoPerceiverBlock
 
     def __init__(self, *, dim: int, depth: int = 6, dim_head: int = 64, heads: int = 8, num_latents: int = 64,
                  max_num_media: Optional[int] = None, max_num_frames: Optional[int] = None, ff_mult: int = 4):
@@ -106,7 +107,8 @@ class OtterPerceiverResampler(nn.Module):
         self.frame_embs = nn.Parameter(torch.randn(max_num_frames, dim)) if exists(max_num_frames) else None
         self.media_time_embs = nn.Parameter(torch.randn(max_num_media, 1, dim)) if exists(max_num_media) else None
         self.layers = nn.ModuleList(
-            [OtterPerceiverBlock(dim=dim, dim_head=dim_head, heads=heads, mult=ff_mult) for _ in range(depth)])
+            [(self._block_cls or OtterPerceiverBlock)(dim=dim, dim_head=dim_head, heads=heads, mult=ff_mult)
+             for _ in range(depth)])
         self.norm = nn.LayerNorm(dim)
 
     def resample_media(self, media2d, BT):
@@ -180,12 +182,14 @@ class OtterMaskedCrossAttention(nn.Module):
 
 class OtterGatedCrossAttentionBlock(nn.Module):
     """reference :343-395 — tanh-gated masked cross-attention + tanh-gated feed-forward."""
+    _attn_cls = None           # Flamingo twin: FlamingoMaskedCrossAttention
 
     def __init__(self, *, dim: int, dim_visual: int, dim_head: int = 64, heads: int = 8, ff_mult: int = 4,
                  only_attend_immediate_media: bool = True):
         super().__init__()
-        self.attn = OtterMaskedCrossAttention(dim=dim, dim_visual=dim_visual, dim_head=dim_head, heads=heads,
-                                              only_attend_immediate_media=only_attend_immediate_media)
+        self.attn = (self._attn_cls or OtterMaskedCrossAttention)(
+            dim=dim, dim_visual=dim_visual, dim_head=dim_head, heads=heads,
+            only_attend_immediate_media=only_attend_immediate_media)
         self.attn_gate = nn.Parameter(torch.tensor([0.0]))
         self.feed_forward = nn.ModuleList(
             [nn.LayerNorm(dim), nn.Linear(dim, dim * ff_mult, bias=False), nn.GELU(),
@@ -284,6 +288,8 @@ def setattr_recursive(obj, att, val):
 
 class OtterLMMixin(nn.Module):
     """reference :445-520 — mixed INTO the language model instance."""
+    _layer_cls = None          # OtterLayer / OtterGatedCrossAttentionBlock (Flamingo twin: its own class names, which
+    _gated_cls = None          # `_no_split_modules` and checkpoints' module reprs refer to)
 
     def set_decoder_layers_attr_name(self, decoder_layers_attr_name):
         self.decoder_layers_attr_name = decoder_layers_attr_name
@@ -301,8 +307,9 @@ class OtterLMMixin(nn.Module):
         for idx, dec in enumerate(layers):
             gated = None
             if (idx + 1) % cross_attn_every_n_layers == 0:
-                gated = OtterGatedCrossAttentionBlock(dim=self.config.hidden_size, dim_visual=vis_hidden_size)
-            wrapped.append(OtterLayer(gated, dec))
+                gated = (self._gated_cls or OtterGatedCrossAttentionBlock)(dim=self.config.hidden_size,
+                                                                           dim_visual=vis_hidden_size)
+            wrapped.append((self._layer_cls or OtterLayer)(gated, dec))
         self._set_decoder_layers(nn.ModuleList(wrapped))
         self.media_token_id = media_token_id
         self.use_media_placement_augmentation = use_media_placement_augmentation

@@ -31,12 +31,11 @@ def master_print(*args, **kwargs):
 
 
 def _reference_lm(arch):
-    """MPT / MosaicGPT / Falcon live in the reference package (frozen LMs, out of scope here)."""
+    """MPT: otter_b200.lm_mpt.  MosaicGPT / Falcon live in the reference package (frozen LMs, out of scope here)."""
+    if arch == "MPTForCausalLM":      # this repo's own MPT on the otter_b200 kernels (SURVEY.md 8f rank 1)
+        from .lm_mpt import MPTConfig, MPTForCausalLM
+        return MPTConfig, MPTForCausalLM, "mosaicml/mpt-7b-instruct"
     try:
-        if arch == "MPTForCausalLM":
-            from otter_ai.models.mpt.configuration_mpt import MPTConfig
-            from otter_ai.models.mpt.modeling_mpt import MPTForCausalLM
-            return MPTConfig, MPTForCausalLM, "mosaicml/mpt-7b-instruct"
         if arch == "MosaicGPT":
             from otter_ai.models.mpt_redpajama.configuration_mosaic_gpt import MosaicGPTConfig
             from otter_ai.models.mpt_redpajama.mosaic_gpt import MosaicGPT
@@ -109,6 +108,7 @@ class _OtterBase(OtterPreTrainedModel):
     _use_frame_embs = True                          # Flamingo builds its perceiver without frame_embs
     _assert_single_frame = False
     _perceiver_cls = OtterPerceiverResampler
+    _lm_mixin_cls = OtterLMMixin
 
     def __init__(self, config: OtterConfig):
         super().__init__(config)
@@ -121,7 +121,7 @@ class _OtterBase(OtterPreTrainedModel):
         self.eoc_token_id = text_tokenizer.encode("<|endofchunk|>")[-1]
         self.media_token_id = text_tokenizer.encode("<image>")[-1]
 
-        extend_instance(lang_encoder, OtterLMMixin)
+        extend_instance(lang_encoder, self._lm_mixin_cls)
         lang_encoder.set_decoder_layers_attr_name(_infer_decoder_layers_attr_name(lang_encoder))
         if self._resize_llama_embeddings and lang_encoder.__class__.__name__ == "LlamaForCausalLM":
             lang_encoder.resize_token_embeddings(len(text_tokenizer))
