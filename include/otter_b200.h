@@ -241,6 +241,19 @@ int otb_fuyu_scatter(const void* word, const void* cont, const int64_t* idx, con
                      int B, int S, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SURVEY.md 8f rank 4 — input pipeline on the device.  Replaces the per-image host transform
+ * Resize((S,S), BICUBIC) -> ToTensor -> Normalize of pipeline/mimicit_utils/mimicit_dataset.py:132-143,329-350
+ * and the fp32 stack + bf16 cast of :510-549 / instruction_following.py:99.
+ * table: device int64 [N][10] = {src ptr (uint8 HWC, 3 channels), H, W, h-bounds offset, h-coefficient offset,
+ * h ksize, v-bounds offset, v-coefficient offset, v ksize, byte offset of this image's [H][S][3] intermediate in tmp};
+ * coef: device int32 pool holding, per distinct (in, out) size pair, bounds [S][2] = (first tap, tap count) and the
+ * 22-bit fixed-point weights [S][ksize] (Pillow's precompute_coeffs + normalize_coeffs_8bpc, computed by the host
+ * binding in float64).  out: [N][3][S][S] bf16 (or fp32).  Bit-exact w.r.t. Pillow / torchvision.  */
+int otb_preprocess_images(const int64_t* table, const int32_t* coef, int N, int max_h, int S, void* tmp, float mean0,
+                          float mean1, float mean2, float std0, float std1, float std2, void* out, int out_fp32,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * SURVEY.md §8f row 2 — the steps immediately either side of the hot path in the training step.
  * Label masking (integer, bit-exact): pipeline/train/instruction_following.py:163-190.
  *   labels = where(ids == eos, eos, mask_val); for every <answer> the span up to and including its matching

@@ -107,6 +107,7 @@ SIGNATURES = {
     "otb_im2col_patches": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _I, _VP]),
     "otb_clip_assemble": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "otb_media_from_clip": (_I, [_VP, _VP, _I, _VP, _I, _I, _I, _VP]),
+    "otb_preprocess_images": (_I, [_VP, _VP, _I, _I, _I, _VP, _F, _F, _F, _F, _F, _F, _VP, _I, _VP]),
     "otb_fuyu_scatter": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
 }
 
