@@ -38,8 +38,9 @@ struct AttnParams {
   // forward outputs
   bf16* out; long long ldo; int o_col0;
   float* lse;  // [P][H][Sq]
-  // mask (mode B) — text_time == nullptr disables masking
-  const int* text_time; int n_per_media; int T_img;
+  // mask (mode B) — text_time == nullptr disables masking; mask_ge: keys of every media slot <= text_time
+  // (only_attend_immediate_media=False, modeling_otter.py:317 mask_op = torch.ge); causal: keys j <= query row
+  const int* text_time; int n_per_media; int T_img; int mask_ge; int causal;
   // backward
   const bf16* o; const bf16* dout; long long ld_do; int do_col0;
   bf16* dq; long long ld_dq; int dq_col0;
@@ -65,6 +66,9 @@ __device__ __forceinline__ KeyTile key_tile(const AttnParams& p, int prob, int j
 // row class: 0 = zeroed row, 1 = normal, 2 = uniform (fully masked)
 __device__ __forceinline__ int row_class(const AttnParams& p, int tt) {
   if (p.text_time == nullptr) return 1;
+  // torch.ge: a row before the first <image> has every key masked -> uniform; it is NOT zeroed afterwards
+  // (the zeroing at modeling_otter.py:326-330 is guarded by only_attend_immediate_media)
+  if (p.mask_ge) return (tt == 0) ? 2 : 1;
   if (tt == 0) return 0;
   return (tt <= p.T_img) ? 1 : 2;
 }
@@ -78,15 +82,20 @@ __device__ __forceinline__ bool key_allowed(const AttnParams& p, int tt, int key
 struct RowRange {
   int lo, hi;
 };
-__device__ __forceinline__ RowRange row_range(const AttnParams& p, int cls, int tt, const KeyTile& kt) {
+__device__ __forceinline__ RowRange row_range(const AttnParams& p, int cls, int tt, const KeyTile& kt, int row) {
   RowRange r;
   r.lo = 0;
   r.hi = (cls == 0) ? 0 : kt.valid;
   if (cls == 1 && p.text_time != nullptr) {
-    const int s0 = (tt - 1) * p.n_per_media - kt.key_base;
-    r.lo = max(0, s0);
-    r.hi = max(r.lo, min(kt.valid, s0 + p.n_per_media));
+    if (p.mask_ge) {                       // media slots 1 .. min(tt, T): one contiguous key prefix
+      r.hi = max(0, min(kt.valid, min(tt, p.T_img) * p.n_per_media - kt.key_base));
+    } else {
+      const int s0 = (tt - 1) * p.n_per_media - kt.key_base;
+      r.lo = max(0, s0);
+      r.hi = max(r.lo, min(kt.valid, s0 + p.n_per_media));
+    }
   }
+  if (p.causal) r.hi = max(r.lo, min(r.hi, row + 1 - kt.key_base));   // self-attention: key index <= query index
   return r;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -194,7 +203,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const bool is_p2 = (nt == 1) || (s >= nt);
     const bool do_max = (nt == 1) || (s < nt);
     const KeyTile kt = key_tile(p, prob, j, nt1);
-    const RowRange rr = row_range(p, cls, tt, kt);
+    const RowRange rr = row_range(p, cls, tt, kt, row);
     if (do_max) {
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -376,7 +385,7 @@ attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     mbar_wait(&bar_s[j], 0);
     tc_fence_after();
     const KeyTile kt = key_tile(p, prob, j, nt1);
-    const RowRange rr = row_range(p, cls, tt, kt);
+    const RowRange rr = row_range(p, cls, tt, kt, row);
     const bool whole = __all_sync(0xffffffffu, cls == 1 && rr.lo == 0 && rr.hi == 128);
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
@@ -410,7 +419,7 @@ attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   const float mb = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
   for (int j = 0; j < nt; ++j) {
     const KeyTile kt = key_tile(p, prob, j, nt1);
-    const RowRange rr = row_range(p, cls, tt, kt);
+    const RowRange rr = row_range(p, cls, tt, kt, row);
     const bool whole = __all_sync(0xffffffffu, cls == 1 && rr.lo == 0 && rr.hi == 128);
     uint8_t* pbuf = s_p + (j & 1) * 2 * kTileBytes;
     if (j >= 2) mbar_wait(&bar_pv[j & 1], 0);          // P buffer (j-2) consumed
@@ -657,7 +666,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (!warp_active) continue;
         tc_fence_after();
         const KeyTile kt = key_tile(p, prob, j, nt1);
-        const RowRange rr = row_range(p, cls, tt, kt);
+        const RowRange rr = row_range(p, cls, tt, kt, row);
         const int nch = (kt.valid + 15) >> 4;
         for (int c = half; c < nch; c += 2) {
           uint32_t r[16];
@@ -691,7 +700,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (g >= 2) mbar_wait(&bar_pv[b], ((g >> 1) - 1) & 1);       // the P V MMA that read this buffer retired
         if (warp_active) {
           const KeyTile kt = key_tile(p, prob, j, nt1);
-          const RowRange rr = row_range(p, cls, tt, kt);
+          const RowRange rr = row_range(p, cls, tt, kt, row);
           const int nch = (kt.valid + 15) >> 4;
           uint8_t* pbuf = s_p + b * 2 * kTileBytes;
           for (int c = half; c < nch; c += 2) {
@@ -863,7 +872,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       const int cls = row_ok ? row_class(p, tt) : 0;
       const float inv_cnt = 1.0f / static_cast<float>(p.Sk1 + p.Sk2);
-      const RowRange rr = row_range(p, cls, tt, kt);
+      const RowRange rr = row_range(p, cls, tt, kt, row);
       const float lse_l2 = lse * 1.4426950408889634f;
 
       if (tid == 0) {
@@ -1039,6 +1048,8 @@ static int check_common(const otb_attn_desc* d) {
   OTB_CHECK_ARG(d->q && d->kv1 && (d->Sk2 == 0 || d->kv2), "otb_attn: null tensor");
   OTB_CHECK_ARG(d->text_time == nullptr || (d->Sk2 == 0 && d->n_per_media > 0 && d->T_img * d->n_per_media == d->Sk1),
                 "otb_attn: media mask needs a single key source with Sk1 == T_img * n_per_media");
+  OTB_CHECK_ARG(!d->causal || (d->Sk2 == 0 && d->Sq == d->Sk1 && d->text_time == nullptr),
+                "otb_attn: causal needs self-attention (Sq == Sk1, one key source, no media mask)");
   return OTB_OK;
 }
 
@@ -1049,6 +1060,7 @@ static void fill_params(const otb_attn_desc* d, AttnParams& p) {
   p.out = static_cast<bf16*>(d->out); p.ldo = d->ld_out; p.o_col0 = d->out_col0;
   p.lse = d->lse;
   p.text_time = d->text_time; p.n_per_media = d->n_per_media; p.T_img = d->T_img;
+  p.mask_ge = d->mask_ge; p.causal = d->causal;
   p.o = static_cast<const bf16*>(d->out);
   p.dout = nullptr; p.dq = nullptr; p.dkv1 = nullptr; p.dkv2 = nullptr; p.dq_ws = nullptr;
   p.ld_do = p.ld_dq = p.ld_dkv1 = p.ld_dkv2 = 0;

@@ -97,7 +97,7 @@ __global__ void epilogue_f32_kernel(const float* __restrict__ acc, const float* 
 struct AttnF32 {
   const float* q; const float* kv1; const float* kv2; float* out; const int* text_time;
   long long ldq, ldkv1, ldkv2, ldo;
-  int q_col0, k1_col0, v1_col0, k2_col0, v2_col0, o_col0, n_per_media, T_img, P, H, Sq, Sk1, Sk2;
+  int q_col0, k1_col0, v1_col0, k2_col0, v2_col0, o_col0, n_per_media, T_img, P, H, Sq, Sk1, Sk2, mask_ge, causal;
   float scale;
 };
 __global__ void __launch_bounds__(64) attn_fwd_f32_kernel(AttnF32 p) {
@@ -113,8 +113,15 @@ __global__ void __launch_bounds__(64) attn_fwd_f32_kernel(AttnF32 p) {
   int cls = 1, tt = 0;
   if (p.text_time != nullptr) {
     tt = p.text_time[grow];
-    cls = (tt == 0) ? 0 : (tt <= p.T_img ? 1 : 2);
+    cls = p.mask_ge ? (tt == 0 ? 2 : 1) : ((tt == 0) ? 0 : (tt <= p.T_img ? 1 : 2));
   }
+  // key j participates (class 1): eq -> slot of j equals tt; ge -> slot of j <= tt; causal -> j <= row
+  auto allowed = [&](int j) {
+    if (p.causal && j > row) return false;
+    if (p.text_time == nullptr) return true;
+    const int slot = j / p.n_per_media + 1;
+    return p.mask_ge ? (slot <= tt) : (slot == tt);
+  };
   float* op = p.out + grow * p.ldo + p.o_col0 + h * 64;
   if (cls == 0) {
 #pragma unroll
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(64) attn_fwd_f32_kernel(AttnF32 p) {
   float m = -INFINITY;
   if (cls == 1) {
     for (int j = 0; j < nk; ++j) {
-      if (p.text_time != nullptr && (j / p.n_per_media + 1) != tt) continue;
+      if (!allowed(j)) continue;
       const float* kp = (j < p.Sk1) ? p.kv1 + (static_cast<long long>(prob) * p.Sk1 + j) * p.ldkv1 + p.k1_col0 + h * 64
                                     : p.kv2 + (static_cast<long long>(prob) * p.Sk2 + (j - p.Sk1)) * p.ldkv2 + p.k2_col0 + h * 64;
       float s = 0.f;
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(64) attn_fwd_f32_kernel(AttnF32 p) {
     if (cls == 2) {
       w = 1.0f;
     } else {
-      if (p.text_time != nullptr && (j / p.n_per_media + 1) != tt) continue;
+      if (!allowed(j)) continue;
       const float* kp = src1 ? p.kv1 + krow * p.ldkv1 + p.k1_col0 + h * 64 : p.kv2 + krow * p.ldkv2 + p.k2_col0 + h * 64;
       float s = 0.f;
 #pragma unroll
@@ -217,7 +224,7 @@ extern "C" int otb_attn_fwd_f32(const otb_attn_desc* d, void* stream) {
   p.kv2 = static_cast<const float*>(d->kv2); p.out = static_cast<float*>(d->out); p.text_time = d->text_time;
   p.ldq = d->ldq; p.ldkv1 = d->ldkv1; p.ldkv2 = d->ldkv2; p.ldo = d->ld_out;
   p.q_col0 = d->q_col0; p.k1_col0 = d->k1_col0; p.v1_col0 = d->v1_col0; p.k2_col0 = d->k2_col0; p.v2_col0 = d->v2_col0;
-  p.o_col0 = d->out_col0; p.n_per_media = d->n_per_media; p.T_img = d->T_img;
+  p.o_col0 = d->out_col0; p.n_per_media = d->n_per_media; p.T_img = d->T_img; p.mask_ge = d->mask_ge; p.causal = d->causal;
   p.P = d->P; p.H = d->H; p.Sq = d->Sq; p.Sk1 = d->Sk1; p.Sk2 = d->Sk2; p.scale = d->scale;
   dim3 grid((d->Sq + 63) / 64, d->H, d->P);
   OTB_CHECK_CUDA(launch_k(attn_fwd_f32_kernel, dim3(grid), dim3(64), 0, ST(stream), p));

@@ -108,6 +108,9 @@ typedef struct otb_attn_desc {
   int32_t n_per_media, T_img;
   int32_t P, H, Sq, Sk1, Sk2, head_dim;
   float scale;
+  int32_t mask_ge; /* media mask with torch.ge instead of torch.eq (only_attend_immediate_media=False, :317): keys of
+                      media slots 1..text_time; rows with text_time == 0 are then uniform, not zeroed (:326 guard) */
+  int32_t causal;  /* self-attention only (Sq == Sk1, no media mask): key j participates iff j <= query row */
 } otb_attn_desc;
 
 typedef struct otb_attn_grads {

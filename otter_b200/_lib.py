@@ -35,7 +35,7 @@ class AttnDesc(C.Structure):
         ("n_per_media", C.c_int32), ("T_img", C.c_int32),
         ("P", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Sk1", C.c_int32), ("Sk2", C.c_int32),
         ("head_dim", C.c_int32),
-        ("scale", C.c_float),
+        ("scale", C.c_float), ("mask_ge", C.c_int32), ("causal", C.c_int32),
     ]
 
 

@@ -209,14 +209,15 @@ class MediaFromClipFn(torch.autograd.Function):
 # OtterGatedCrossAttentionBlock (:343-395) incl. OtterMaskedCrossAttention (:238-340)
 # =================================================================================================
 def masked_cross_attention_fwd(x, media, tt, B, L, Tn, n, T_img, heads, norm_w, norm_b, wq, wkv, wo, *, gate=None,
-                               residual=None, want_lse=True):
+                               residual=None, want_lse=True, mask_ge=False):
     """Shared by the standalone OtterMaskedCrossAttention module and the gated block.
     Returns (out, saved) where out = (o Wo^T) [* tanh(gate) + residual]."""
     inner = heads * 64
     xn, mx, rx = F.layernorm_fwd(x, f32_of(norm_w), f32_of(norm_b))                           # :283
     q = F.linear_fwd(xn, bf16_of(wq))                                                         # :285
     kv = F.linear_fwd(media, bf16_of(wkv))                                                    # :286-288
-    spec = F.AttnSpec(q, 0, kv, 0, inner, B, heads, L, Tn, 0.125, text_time=tt, n_per_media=n, T_img=T_img)
+    spec = F.AttnSpec(q, 0, kv, 0, inner, B, heads, L, Tn, 0.125, text_time=tt, n_per_media=n, T_img=T_img,
+                      mask_ge=mask_ge)
     o, lse = F.attn_fwd(spec, want_lse=want_lse)                                              # :290-333 fused
     a = None
     if gate is not None:
@@ -231,27 +232,28 @@ class MaskedCrossAttentionFn(torch.autograd.Function):
     """Standalone OtterMaskedCrossAttention.forward (:262-340): x [B*L,D], media [B*T*n,Dv] -> [B*L,D]."""
 
     @staticmethod
-    def forward(ctx, x, media, tt, B, L, T_img, n, heads, norm_w, norm_b, wq, wkv, wo):
+    def forward(ctx, x, media, tt, B, L, T_img, n, heads, norm_w, norm_b, wq, wkv, wo, mask_ge=False):
         out, saved = masked_cross_attention_fwd(x, media, tt, B, L, T_img * n, n, T_img, heads, norm_w, norm_b, wq,
-                                                wkv, wo)
+                                                wkv, wo, mask_ge=mask_ge)
         xn, mx, rx, q, kv, o, lse, _ = saved
         ctx.save_for_backward(x, media, tt, xn, mx, rx, q, kv, o, lse)
         ctx.params = (norm_w, norm_b, wq, wkv, wo)
-        ctx.cfg = (B, L, T_img, n, heads)
+        ctx.cfg = (B, L, T_img, n, heads, mask_ge)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, media, tt, xn, mx, rx, q, kv, o, lse = ctx.saved_tensors
         norm_w, norm_b, wq, wkv, wo = ctx.params
-        B, L, T_img, n, heads = ctx.cfg
+        B, L, T_img, n, heads, mask_ge = ctx.cfg
         inner = heads * 64
         sink = GradSink()
         dout = _as_bf16_2d(dout, wo.shape[0])
         g, acc = sink.target(wo)
         F.linear_wgrad(dout, o, out=g, accumulate=acc)
         do = F.linear_dgrad(dout, bf16_of(wo))
-        spec = F.AttnSpec(q, 0, kv, 0, inner, B, heads, L, T_img * n, 0.125, text_time=tt, n_per_media=n, T_img=T_img)
+        spec = F.AttnSpec(q, 0, kv, 0, inner, B, heads, L, T_img * n, 0.125, text_time=tt, n_per_media=n, T_img=T_img,
+                          mask_ge=mask_ge)
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
         F.attn_bwd(spec, o, 0, lse, do, 0, dq, 0, dkv, 0, inner)
         g, acc = sink.target(wq)
@@ -264,7 +266,7 @@ class MaskedCrossAttentionFn(torch.autograd.Function):
         gb, _ = sink.target(norm_b)
         dx, _, _ = F.layernorm_bwd(dxn, x, mx, rx, f32_of(norm_w), dgamma=gw, dbeta=gb, accumulate=acc)
         r = sink.result
-        return dx, dmedia, None, None, None, None, None, None, r(norm_w), r(norm_b), r(wq), r(wkv), r(wo)
+        return dx, dmedia, None, None, None, None, None, None, r(norm_w), r(norm_b), r(wq), r(wkv), r(wo), None
 
 
 class GatedCrossAttentionBlockFn(torch.autograd.Function):
@@ -272,9 +274,9 @@ class GatedCrossAttentionBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, media, tt, B, L, T_img, n, heads, norm_w, norm_b, wq, wkv, wo, attn_gate, ff_w, ff_b, w1, w2,
-                ff_gate):
+                ff_gate, mask_ge=False):
         x1, saved = masked_cross_attention_fwd(x, media, tt, B, L, T_img * n, n, T_img, heads, norm_w, norm_b, wq,
-                                               wkv, wo, gate=attn_gate, residual=x)           # :380-389
+                                               wkv, wo, gate=attn_gate, residual=x, mask_ge=mask_ge)   # :380-389
         xn, mx, rx, q, kv, o, lse, a1 = saved
         h0, mf, rf = F.layernorm_fwd(x1, f32_of(ff_w), f32_of(ff_b))                          # :391-392
         z = torch.empty((x.shape[0], w1.shape[0]), device=x.device, dtype=BF16)
@@ -284,14 +286,14 @@ class GatedCrossAttentionBlockFn(torch.autograd.Function):
         tt_s = tt if tt is not None else torch.empty(0, device=x.device, dtype=torch.int32)
         ctx.save_for_backward(x, media, tt_s, xn, mx, rx, q, kv, o, lse, a1, x1, h0, mf, rf, z, hh, a2)
         ctx.params = (norm_w, norm_b, wq, wkv, wo, attn_gate, ff_w, ff_b, w1, w2, ff_gate)
-        ctx.cfg = (B, L, T_img, n, heads, tt is not None)
+        ctx.cfg = (B, L, T_img, n, heads, tt is not None, mask_ge)
         return x2
 
     @staticmethod
     def backward(ctx, dx2):
         x, media, tt, xn, mx, rx, q, kv, o, lse, a1, x1, h0, mf, rf, z, hh, a2 = ctx.saved_tensors
         norm_w, norm_b, wq, wkv, wo, attn_gate, ff_w, ff_b, w1, w2, ff_gate = ctx.params
-        B, L, T_img, n, heads, has_tt = ctx.cfg
+        B, L, T_img, n, heads, has_tt, mask_ge = ctx.cfg
         tt = tt if has_tt else None
         D = x.shape[1]
         inner = heads * 64
@@ -317,7 +319,8 @@ class GatedCrossAttentionBlockFn(torch.autograd.Function):
         go, acco = sink.target(wo)
         ws.run(lambda: F.linear_wgrad(dx1, o, out=go, accumulate=acco, scale_ptr=ag, scale_tanh=True))
         do = F.linear_dgrad(dx1, bf16_of(wo), scale_ptr=ag, scale_tanh=True)
-        spec = F.AttnSpec(q, 0, kv, 0, inner, B, heads, L, T_img * n, 0.125, text_time=tt, n_per_media=n, T_img=T_img)
+        spec = F.AttnSpec(q, 0, kv, 0, inner, B, heads, L, T_img * n, 0.125, text_time=tt, n_per_media=n, T_img=T_img,
+                          mask_ge=mask_ge)
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
         F.attn_bwd(spec, o, 0, lse, do, 0, dq, 0, dkv, 0, inner)
         gq, accq = sink.target(wq)
@@ -336,7 +339,7 @@ class GatedCrossAttentionBlockFn(torch.autograd.Function):
         ws.join()
         r = sink.result
         return (dx, dmedia, None, None, None, None, None, None, r(norm_w), r(norm_b), r(wq), r(wkv), r(wo),
-                r(attn_gate), r(ff_w), r(ff_b), r(w1), r(w2), r(ff_gate))
+                r(attn_gate), r(ff_w), r(ff_b), r(w1), r(w2), r(ff_gate), None)
 
 
 # =================================================================================================

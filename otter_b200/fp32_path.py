@@ -109,7 +109,7 @@ def masked_cross_attention(att, x2d, media2d, tt, B, L, T_img, n, gate=None, res
     q = lin(xn, att.to_q.weight)
     kv = lin(media2d, att.to_kv.weight)
     spec = F.AttnSpec(q, 0, kv, 0, inner, B, att.heads, L, T_img * n, 0.125, text_time=tt, n_per_media=n, T_img=T_img,
-                      dtype=torch.float32)
+                      dtype=torch.float32, mask_ge=not att.only_attend_immediate_media)
     o = F.attn_fwd_f32(spec)
     if gate is None:
         return lin(o, att.to_out.weight)

@@ -247,13 +247,14 @@ class AttnSpec:
     """Where Q / K / V / O live inside their 2-D buffers (see otb_attn_desc)."""
 
     def __init__(self, q, q_col0, kv1, k1_col0, v1_col0, P, H, Sq, Sk1, scale, kv2=None, k2_col0=0, v2_col0=0, Sk2=0,
-                 text_time=None, n_per_media=0, T_img=0, dtype=BF16):
+                 text_time=None, n_per_media=0, T_img=0, dtype=BF16, mask_ge=False, causal=False):
         self.q, self.q_col0 = _mat(q, "q", dtype), q_col0
         self.kv1, self.k1_col0, self.v1_col0 = _mat(kv1, "kv1", dtype), k1_col0, v1_col0
         self.kv2 = _mat(kv2, "kv2", dtype) if kv2 is not None else None
         self.k2_col0, self.v2_col0 = k2_col0, v2_col0
         self.P, self.H, self.Sq, self.Sk1, self.Sk2, self.scale = P, H, Sq, Sk1, Sk2, scale
         self.text_time, self.n_per_media, self.T_img = text_time, n_per_media, T_img
+        self.mask_ge, self.causal = bool(mask_ge), bool(causal)
         assert self.q.shape[0] == P * Sq and self.kv1.shape[0] == P * Sk1
         if text_time is not None:
             _req(text_time, torch.int32, "text_time")
@@ -273,6 +274,7 @@ class AttnSpec:
         d.n_per_media, d.T_img = self.n_per_media, self.T_img
         d.P, d.H, d.Sq, d.Sk1, d.Sk2, d.head_dim = self.P, self.H, self.Sq, self.Sk1, self.Sk2, 64
         d.scale = self.scale
+        d.mask_ge, d.causal = int(self.mask_ge), int(self.causal)
         return d
 
 

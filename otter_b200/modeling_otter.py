@@ -151,9 +151,6 @@ class OtterMaskedCrossAttention(nn.Module):
                  only_attend_immediate_media: bool = True):
         super().__init__()
         _check_heads(dim_head)
-        if not only_attend_immediate_media:
-            raise NotImplementedError("only_attend_immediate_media=False is never used by Otter (init_otter "
-                                      "keeps the default, modeling_otter.py:472-475) and is not built")
         self.scale = dim_head ** -0.5
         self.heads = heads
         inner_dim = dim_head * heads
@@ -176,7 +173,7 @@ class OtterMaskedCrossAttention(nn.Module):
             return out.view(B, L, D).to(x.dtype)
         out = MaskedCrossAttentionFn.apply(_as_bf16_2d(x, D), _as_bf16_2d(media, media.shape[-1]), tt, B, L, T_img, n,
                                            self.heads, self.norm.weight, self.norm.bias, self.to_q.weight,
-                                           self.to_kv.weight, self.to_out.weight)
+                                           self.to_kv.weight, self.to_out.weight, not self.only_attend_immediate_media)
         return out.view(B, L, D).to(x.dtype)
 
 
@@ -200,7 +197,8 @@ class OtterGatedCrossAttentionBlock(nn.Module):
         a, ff = self.attn, self.feed_forward
         return GatedCrossAttentionBlockFn.apply(x2d, media2d, tt, B, L, T_img, n, a.heads, a.norm.weight, a.norm.bias,
                                                 a.to_q.weight, a.to_kv.weight, a.to_out.weight, self.attn_gate,
-                                                ff[0].weight, ff[0].bias, ff[1].weight, ff[3].weight, self.ff_gate)
+                                                ff[0].weight, ff[0].bias, ff[1].weight, ff[3].weight, self.ff_gate,
+                                                not a.only_attend_immediate_media)
 
     def forward(self, x: torch.Tensor, media: torch.Tensor, media_locations: Optional[torch.BoolTensor] = None,
                 attend_previous: bool = True) -> torch.Tensor:

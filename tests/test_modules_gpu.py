@@ -387,3 +387,35 @@ def test_backward_is_deterministic():
         out.float().pow(2).mean().backward()
         runs.append([out.detach().clone()] + [p.grad.clone() for p in list(rs.parameters()) + list(gb.parameters())])
     assert all(torch.equal(a, b) for a, b in zip(*runs))
+
+
+@pytest.mark.parametrize("pos,T,attend_previous", [([[0, 12], [3, 20]], 2, True), ([[5], []], 1, True),
+                                                    ([[0, 8, 16], [2, 9]], 2, False)])
+def test_masked_cross_attention_attend_all_previous_media(pos, T, attend_previous):
+    """only_attend_immediate_media=False (reference :246,317: mask_op = torch.ge; no zeroing of rows, :326 guard):
+    fwd + bwd against the oracle in production mode, forward in fp32-grade mode at the north-star tolerance."""
+    import otter_b200
+    from otter_b200.modeling_otter import OtterMaskedCrossAttention
+    torch.manual_seed(7)
+    B, L, D, Dv, n = 2, 32, 256, 128, 64
+    att = OtterMaskedCrossAttention(dim=D, dim_visual=Dv, only_attend_immediate_media=False).to(DEV)
+    x = torch.randn(B, L, D, device=DEV).requires_grad_(True)
+    media = torch.randn(B, T, n, Dv, device=DEV).requires_grad_(True)
+    loc = torch.zeros(B, L, dtype=torch.bool)
+    for b, ps in enumerate(pos):
+        loc[b, ps] = True
+    p = {k: v.detach().float().cpu().requires_grad_(True) for k, v in att.state_dict().items()}
+    xr, mr = x.detach().cpu().requires_grad_(True), media.detach().cpu().requires_grad_(True)
+    ref = R.masked_cross_attention(xr, mr, loc, p, attend_previous=attend_previous, only_attend_immediate_media=False)
+    wgt = torch.randn(B, L, D)
+    (ref * wgt).sum().backward()
+    out = att(x, media, media_locations=loc.to(DEV), attend_previous=attend_previous)
+    (out.float() * wgt.to(DEV)).sum().backward()
+    check_out(out, ref.detach(), "xattn ge")
+    check_out(x.grad, xr.grad, "xattn ge dx", fro=3e-2, mx=6e-2)
+    check_out(media.grad, mr.grad, "xattn ge dmedia", fro=3e-2, mx=6e-2)
+    for k, v in att.named_parameters():
+        check_out(v.grad, p[k].grad, f"xattn ge grad {k}", fro=4e-2, mx=1e-1)
+    with torch.no_grad(), otter_b200.precision("fp32"):
+        out32 = att(x.detach(), media.detach(), media_locations=loc.to(DEV), attend_previous=attend_previous)
+    ns_close(out32, ref.detach(), "xattn ge fp32-grade")
