@@ -110,20 +110,31 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, float scale, ui
           o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
           *reinterpret_cast<uint4*>(ep.aux_out + lrow * ep.ld_aux_out + col) = o;
         }
-        if (ep.act == 1) {
+        if (ep.aux_in == nullptr) {
+          if (ep.act == 1) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
-        } else if (ep.act == 2) {
+            for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
+          } else if (ep.act == 2) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
-        }
-        if (ep.aux_in != nullptr) {
+            for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
+          } else if (ep.act == 3) {                     // relu^2 (Persimmon "relu2")
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float r_ = fmaxf(v[i], 0.f); v[i] = r_ * r_; }
+          }
+        } else {   // backward of the activation whose pre-activation is aux_in: act 3 -> 2 relu(z), otherwise gelu'(z)
           const float2 a0 = unpack_bf16x2(aux[g].x), a1 = unpack_bf16x2(aux[g].y), a2 = unpack_bf16x2(aux[g].z),
                        a3 = unpack_bf16x2(aux[g].w);
-          v[0] *= gelu_grad_fast(a0.x); v[1] *= gelu_grad_fast(a0.y);
-          v[2] *= gelu_grad_fast(a1.x); v[3] *= gelu_grad_fast(a1.y);
-          v[4] *= gelu_grad_fast(a2.x); v[5] *= gelu_grad_fast(a2.y);
-          v[6] *= gelu_grad_fast(a3.x); v[7] *= gelu_grad_fast(a3.y);
+          if (ep.act == 3) {
+            v[0] *= 2.f * fmaxf(a0.x, 0.f); v[1] *= 2.f * fmaxf(a0.y, 0.f);
+            v[2] *= 2.f * fmaxf(a1.x, 0.f); v[3] *= 2.f * fmaxf(a1.y, 0.f);
+            v[4] *= 2.f * fmaxf(a2.x, 0.f); v[5] *= 2.f * fmaxf(a2.y, 0.f);
+            v[6] *= 2.f * fmaxf(a3.x, 0.f); v[7] *= 2.f * fmaxf(a3.y, 0.f);
+          } else {
+            v[0] *= gelu_grad_fast(a0.x); v[1] *= gelu_grad_fast(a0.y);
+            v[2] *= gelu_grad_fast(a1.x); v[3] *= gelu_grad_fast(a1.y);
+            v[4] *= gelu_grad_fast(a2.x); v[5] *= gelu_grad_fast(a2.y);
+            v[6] *= gelu_grad_fast(a3.x); v[7] *= gelu_grad_fast(a3.y);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] *= scale;
@@ -224,20 +235,31 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, float scale
           x.z = pack_bf16x2(v[4], v[5]); x.w = pack_bf16x2(v[6], v[7]);
           *reinterpret_cast<uint4*>(ep.aux_out + lrow * ep.ld_aux_out + col) = x;
         }
-        if (ep.act == 1) {
+        if (ep.aux_in == nullptr) {
+          if (ep.act == 1) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
-        } else if (ep.act == 2) {
+            for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
+          } else if (ep.act == 2) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
-        }
-        if (ep.aux_in != nullptr) {
+            for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
+          } else if (ep.act == 3) {                     // relu^2 (Persimmon "relu2")
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float r_ = fmaxf(v[i], 0.f); v[i] = r_ * r_; }
+          }
+        } else {   // backward of the activation whose pre-activation is aux_in: act 3 -> 2 relu(z), otherwise gelu'(z)
           const float2 a0 = unpack_bf16x2(aux[g].x), a1 = unpack_bf16x2(aux[g].y), a2 = unpack_bf16x2(aux[g].z),
                        a3 = unpack_bf16x2(aux[g].w);
-          v[0] *= gelu_grad_fast(a0.x); v[1] *= gelu_grad_fast(a0.y);
-          v[2] *= gelu_grad_fast(a1.x); v[3] *= gelu_grad_fast(a1.y);
-          v[4] *= gelu_grad_fast(a2.x); v[5] *= gelu_grad_fast(a2.y);
-          v[6] *= gelu_grad_fast(a3.x); v[7] *= gelu_grad_fast(a3.y);
+          if (ep.act == 3) {
+            v[0] *= 2.f * fmaxf(a0.x, 0.f); v[1] *= 2.f * fmaxf(a0.y, 0.f);
+            v[2] *= 2.f * fmaxf(a1.x, 0.f); v[3] *= 2.f * fmaxf(a1.y, 0.f);
+            v[4] *= 2.f * fmaxf(a2.x, 0.f); v[5] *= 2.f * fmaxf(a2.y, 0.f);
+            v[6] *= 2.f * fmaxf(a3.x, 0.f); v[7] *= 2.f * fmaxf(a3.y, 0.f);
+          } else {
+            v[0] *= gelu_grad_fast(a0.x); v[1] *= gelu_grad_fast(a0.y);
+            v[2] *= gelu_grad_fast(a1.x); v[3] *= gelu_grad_fast(a1.y);
+            v[4] *= gelu_grad_fast(a2.x); v[5] *= gelu_grad_fast(a2.y);
+            v[6] *= gelu_grad_fast(a3.x); v[7] *= gelu_grad_fast(a3.y);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] *= scale;
@@ -691,7 +713,7 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   OTB_CHECK_ARG(e->aux_out == nullptr || (e->ld_aux_out % 8 == 0 && e->ld_aux_out >= N),
                 "otb_gemm_bf16: bad ld_aux_out");
   OTB_CHECK_ARG(e->residual == nullptr || (e->ld_res % 8 == 0 && e->ld_res >= N), "otb_gemm_bf16: bad ld_res");
-  OTB_CHECK_ARG(e->act >= 0 && e->act <= 2, "otb_gemm_bf16: bad act");
+  OTB_CHECK_ARG(e->act >= 0 && e->act <= 3, "otb_gemm_bf16: bad act");
   if (a_mn_major) OTB_CHECK_ARG(M % 8 == 0 && lda >= M, "otb_gemm_bf16: MN-major A needs M%%8==0, lda>=M");
   else OTB_CHECK_ARG(lda >= K, "otb_gemm_bf16: lda < K");
   if (b_mn_major) OTB_CHECK_ARG(ldb >= N, "otb_gemm_bf16: ldb < N");

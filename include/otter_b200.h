@@ -56,8 +56,11 @@ int otb_abi_sizeof(int which);
  * Epilogue (all optional, applied in this order on the fp32 accumulator v):
  *   v += bias[n]                                   (fp32 [N])
  *   aux_out[m,n] = bf16(v)                         (pre-activation, kept for backward)
- *   v = act(v)             act: 0 none, 1 GELU(erf) (modeling_otter.py:146,367), 2 quick-GELU (CLIP)
- *   v *= gelu'(aux_in[m,n])                        (backward of GELU, aux_in = saved pre-activation)
+ *   v = act(v)             act: 0 none, 1 GELU(erf) (modeling_otter.py:146,367), 2 quick-GELU (CLIP),
+ *                               3 relu(v)^2 (Persimmon "relu2", fuyu/modeling_persimmon.py:187-193) — skipped when
+ *                               aux_in is given: then `act` names the activation whose DERIVATIVE is applied
+ *   v *= act'(aux_in[m,n])                         (backward: aux_in = saved pre-activation; act 3 -> 2 relu(z),
+ *                                                   any other value -> gelu'(z))
  *   v *= alpha * (scale_ptr ? (scale_tanh ? tanh(*scale_ptr) : *scale_ptr) : 1)
  *                                                  (tanh gate, modeling_otter.py:387-388,393)
  *   v += residual[m,n]                             (bf16)
@@ -242,6 +245,23 @@ int otb_media_from_clip(const void* hidden, const float* frame_embs, int F, void
  * read out of bounds (the host wrapper raises the reference's ValueError for them before launching). */
 int otb_fuyu_scatter(const void* word, const void* cont, const int64_t* idx, const int64_t* b_off, void* out,
                      int B, int S, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SURVEY.md 8f rank 3 — Persimmon / Fuyu decoder layer: split + qk-LayerNorm + partial rotary embedding.
+ * Replaces fuyu/modeling_persimmon.py:277-303 (`_split_heads`, fused_layer_norm on q and k, fused_apply_rotary_emb on
+ * the first rotary_dims of every head, non-interleaved).  fused: bf16 [rows][H][3][64] (query_key_value output);
+ * qkv: bf16 [rows][3*H*64] = q | k | v column blocks, head h at columns h*64 of its block (the layout otb_attn_* reads);
+ * stats: fp32 [rows][H][4] = mean_q, rstd_q, mean_k, rstd_k (kept for backward); position of a row = row % S.
+ * Backward: dqkv -> dfused (same layouts) and the four [64] affine gradients through a deterministic two-stage
+ * reduction; ws: otb_qkln_rope_ws_floats() floats. */
+int otb_qkln_rope_ws_floats(void);
+int otb_qkln_rope_fwd(const void* fused, int64_t ld_fused, const float* q_gamma, const float* q_beta,
+                      const float* k_gamma, const float* k_beta, void* qkv, int64_t ld_qkv, float* stats, int64_t rows,
+                      int H, int S, int rotary_dims, float rope_theta, float eps, void* stream);
+int otb_qkln_rope_bwd(const void* dqkv, int64_t ld_dqkv, const void* fused, int64_t ld_fused, const float* stats,
+                      const float* q_gamma, const float* k_gamma, void* dfused, int64_t ld_dfused, float* dq_gamma,
+                      float* dq_beta, float* dk_gamma, float* dk_beta, int accumulate, float* ws, int64_t rows, int H,
+                      int S, int rotary_dims, float rope_theta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SURVEY.md 8f rank 4 — input pipeline on the device.  Replaces the per-image host transform

@@ -107,6 +107,10 @@ SIGNATURES = {
     "otb_im2col_patches": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _I, _VP]),
     "otb_clip_assemble": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "otb_media_from_clip": (_I, [_VP, _VP, _I, _VP, _I, _I, _I, _VP]),
+    "otb_qkln_rope_ws_floats": (_I, []),
+    "otb_qkln_rope_fwd": (_I, [_VP, _I64, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _I64, _I, _I, _I, _F, _F, _VP]),
+    "otb_qkln_rope_bwd": (_I, [_VP, _I64, _VP, _I64, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _I, _VP, _I64, _I, _I,
+                               _I, _F, _VP]),
     "otb_preprocess_images": (_I, [_VP, _VP, _I, _I, _I, _VP, _F, _F, _F, _F, _F, _F, _VP, _I, _VP]),
     "otb_fuyu_scatter": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
 }

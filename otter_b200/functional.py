@@ -458,6 +458,40 @@ def fuyu_scatter(word, cont, idx, b_off):
 
 
 # ------------------------------------------------------------------------------------------------
+# Persimmon / Fuyu layer: split + qk-LayerNorm + partial RoPE (csrc/otb_persimmon.cu)
+# ------------------------------------------------------------------------------------------------
+@_on_device
+def qkln_rope_fwd(fused, H, S, q_gamma, q_beta, k_gamma, k_beta, rotary_dims, rope_theta, eps=1e-5):
+    """fused bf16 [rows, H*3*64] -> (qkv bf16 [rows, 3*H*64] as q | k | v blocks, stats fp32 [rows, H, 4])."""
+    fused = _mat(fused, "fused")
+    rows = fused.shape[0]
+    assert fused.shape[1] == H * 192, fused.shape
+    qkv = torch.empty((rows, 3 * H * 64), device=fused.device, dtype=BF16)
+    stats = torch.empty((rows, H, 4), device=fused.device, dtype=torch.float32)
+    check(_lib.load().otb_qkln_rope_fwd(_p(fused), fused.stride(0), _p(_req(q_gamma, torch.float32)),
+                                        _p(_req(q_beta, torch.float32)), _p(_req(k_gamma, torch.float32)),
+                                        _p(_req(k_beta, torch.float32)), _p(qkv), qkv.stride(0), _p(stats), rows, H, S,
+                                        int(rotary_dims), float(rope_theta), float(eps), _stream()), "otb_qkln_rope_fwd")
+    return qkv, stats
+
+
+@_on_device
+def qkln_rope_bwd(dqkv, fused, stats, H, S, q_gamma, k_gamma, rotary_dims, rope_theta, dq_gamma, dq_beta, dk_gamma,
+                  dk_beta, accumulate=False):
+    """-> dfused bf16 [rows, H*3*64]; the four fp32 [64] parameter gradients are written / accumulated in place."""
+    lib = _lib.load()
+    dqkv, fused = _mat(dqkv, "dqkv"), _mat(fused, "fused")
+    rows = fused.shape[0]
+    dfused = torch.empty_like(fused)
+    ws = torch.empty(lib.otb_qkln_rope_ws_floats(), device=fused.device, dtype=torch.float32)
+    check(lib.otb_qkln_rope_bwd(_p(dqkv), dqkv.stride(0), _p(fused), fused.stride(0), _p(stats), _p(q_gamma), _p(k_gamma),
+                                _p(dfused), dfused.stride(0), _p(dq_gamma), _p(dq_beta), _p(dk_gamma), _p(dk_beta),
+                                int(bool(accumulate)), _p(ws), rows, H, S, int(rotary_dims), float(rope_theta), _stream()),
+          "otb_qkln_rope_bwd")
+    return dfused
+
+
+# ------------------------------------------------------------------------------------------------
 # fp32-grade forward path (parity mode; csrc/otb_fp32.cu)
 # ------------------------------------------------------------------------------------------------
 F32_KCHUNK = 512

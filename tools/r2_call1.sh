@@ -25,10 +25,12 @@ export OTB_ATTN_WS=0
 
 # 1. new parity tests first (the round-1 verdict's hole), then the default full suite
 TMO=600 run pytest_c2_parity -- python -m pytest tests/test_c2_parity_gpu.py -m gpu -x -q
-TMO=900 run pytest_default_full -- python -m pytest tests -m gpu -q --ignore tests/test_lm_gpu.py --ignore tests/test_callers_gpu.py --ignore tests/test_data_gpu.py
+TMO=900 run pytest_default_full -- python -m pytest tests -m gpu -q --ignore tests/test_lm_gpu.py --ignore tests/test_callers_gpu.py --ignore tests/test_data_gpu.py --ignore tests/test_persimmon_gpu.py --ignore tests/test_multi_device_gpu.py
 run pytest_lm -- python -m pytest tests/test_lm_gpu.py -m gpu -x -q
 run pytest_callers -- python -m pytest tests/test_callers_gpu.py -m gpu -q
 run pytest_data -- python -m pytest tests/test_data_gpu.py -m gpu -q
+run pytest_persimmon -- python -m pytest tests/test_persimmon_gpu.py -m gpu -q
+run pytest_multidev -- python -m pytest tests/test_multi_device_gpu.py -m gpu -q
 
 # 2. GEMM self-test + micro-bench under each epilogue / dispatch setting
 run selftest_default -- build/selftest_gemm --bench
