@@ -151,9 +151,13 @@ class HotPath:
         self.cfg, self.batch, self.dev, self.rank, self.world, self.args = cfg, batch, dev, rank, world, args
         self.clip, self.perceiver, self.gated = build_modules(dev, cfg)
         self.trainable = list(self.perceiver.parameters()) + list(self.gated.parameters())
-        comm_dtype = torch.bfloat16 if args.grad_comm_dtype == "bf16" else None
+        comm_dtype = torch.bfloat16 if args.grad_comm_dtype.startswith("bf16") else None
+        direct = None
+        if args.grad_comm_dtype == "bf16-direct":      # the Linear weights' wgrad epilogues write the wire buffer
+            direct = [m.weight for mod in (self.perceiver, self.gated) for m in mod.modules()
+                      if isinstance(m, torch.nn.Linear)]
         self.flat = FlatGradBuffer(self.trainable, device=dev, comm_dtype=comm_dtype,
-                                   nccl_registered=args.nccl_registered and world > 1)
+                                   nccl_registered=args.nccl_registered and world > 1, direct_params=direct)
         self.h_vis, self.h_hid, self.h_loc = host_batch(batch, rank, cfg)
         self.d_vis, self.d_hid, self.d_loc = self.h_vis.to(dev), self.h_hid.to(dev), self.h_loc.to(dev)
         self.loss_host = torch.zeros(1).pin_memory()
@@ -886,7 +890,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--multi-cast", action="store_true", default=os.environ.get("OTB_MULTI_CAST") == "1",
                     help="re-derive the bf16 weight copies in one multi-tensor launch")
-    ap.add_argument("--grad-comm-dtype", default="fp32", choices=["fp32", "bf16"],
+    ap.add_argument("--grad-comm-dtype", default="fp32", choices=["fp32", "bf16", "bf16-direct"],
                     help="wire format of the single gradient all-reduce (gradients stay fp32 on both sides); bf16 "
                          "halves the payload to SURVEY.md §8e's 2.36 GB at the cost of two cast passes per step")
     ap.add_argument("--e2e-prefetch", action="store_true",

@@ -29,10 +29,23 @@ class _CommHandle:
 
 
 class FlatGradBuffer:
-    def __init__(self, params, device=None, dtype=torch.float32, comm_dtype=None, nccl_registered=False):
+    def __init__(self, params, device=None, dtype=torch.float32, comm_dtype=None, nccl_registered=False,
+                 direct_params=None):
+        """direct_params (only with a reduced-precision comm_dtype): parameters whose gradient is produced by ONE wgrad
+        GEMM per step (the nn.Linear weights of the perceiver / gated blocks).  Their kernel sink is the bf16 WIRE
+        buffer itself — the epilogue rounds once to the wire format, which is also what autocast's backward hands the
+        reference (a bf16 weight gradient cast up to fp32) — so the 7 GB cast pass in front of the collective
+        disappears; `.grad` (fp32) is filled by the one up-cast after the collective.  Gradient accumulation over
+        several backward passes per step is not available for these parameters (the sink refuses a second write)."""
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
+        direct_ids = {id(p) for p in (direct_params or [])}
+        if direct_ids and (comm_dtype is None or comm_dtype == dtype):
+            raise ValueError("direct_params needs a reduced-precision comm_dtype")
+        # direct-sink parameters first, so that everything still produced in fp32 is ONE contiguous tail to cast
+        self.params = [p for p in self.params if id(p) in direct_ids] + [p for p in self.params if id(p) not in direct_ids]
+        self.n_direct_params = sum(1 for p in self.params if id(p) in direct_ids)
         device = device or self.params[0].device
         # 16-byte aligned segments so vectorised epilogue stores stay legal
         self.offsets, off = [], 0
@@ -40,6 +53,9 @@ class FlatGradBuffer:
             self.offsets.append(off)
             off += (p.numel() + 3) // 4 * 4
         self.numel = off
+        self.direct_numel = self.offsets[self.n_direct_params] if self.n_direct_params < len(self.params) else off
+        if self.n_direct_params == 0:
+            self.direct_numel = 0
         self._pools = []
         self._registered = bool(nccl_registered)
         self.flat = self._alloc(off, dtype, device)
@@ -58,6 +74,8 @@ class FlatGradBuffer:
             if dtype == torch.float32:
                 p._otb_grad = view          # sink used by otter_b200 backward kernels
                 p._otb_grad_live = False
+        for p, o in zip(self.params[:self.n_direct_params], self.offsets):
+            p._otb_grad = self.comm[o:o + p.numel()].view(p.shape)      # the wgrad epilogue writes the wire format
 
     def _alloc(self, n, dtype, device):
         """Plain zero-filled allocation, or (nccl_registered=True) one drawn from NCCL's own allocator and registered
@@ -100,7 +118,7 @@ class FlatGradBuffer:
         for p, view in zip(self.params, self.views):
             sink = getattr(p, "_otb_sink_user", False)
             if sink and not p._otb_grad_live:
-                view.zero_()
+                p._otb_grad.zero_()
             g = p.grad
             if g is None or g.data_ptr() != view.data_ptr():
                 if g is not None and not sink:
@@ -110,9 +128,15 @@ class FlatGradBuffer:
     def all_reduce(self, group=None, async_op=False):
         """The one collective of the step: mean over ranks (DDP semantics)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            if self.direct_numel:       # single rank: the wire-format sinks still have to reach the fp32 `.grad` views
+                self.flat[:self.direct_numel].copy_(self.comm[:self.direct_numel])
             return None
         if self.comm is not None:
-            self.comm.copy_(self.flat)                 # cast on the current stream, ahead of the collective
+            # cast on the current stream, ahead of the collective: everything, or only the fp32-produced tail when the
+            # big gradients were written in the wire format by the kernels
+            d = self.direct_numel
+            if d < self.numel:
+                self.comm[d:].copy_(self.flat[d:])
             if dist.get_backend(group) == "gloo":
                 w = dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
                 h = _CommHandle(self, w if async_op else None, dist.get_world_size(group))

@@ -138,6 +138,9 @@ class GradSink:
         buf = getattr(p, "_otb_grad", None)
         if buf is not None:
             acc = bool(getattr(p, "_otb_grad_live", False)) and bool(getattr(p, "_otb_sink_user", False))
+            if acc and buf.dtype != torch.float32:
+                raise RuntimeError("a wire-format (bf16) gradient sink takes one write per step: gradient accumulation "
+                                   "over several backward passes needs FlatGradBuffer without direct_params")
             p._otb_grad_live = True
             p._otb_sink_user = True
             return buf, acc

@@ -121,3 +121,53 @@ def test_zero_grad_set_to_none_keeps_the_flat_buffer_live():
         for p, b in zip(lin.parameters(), before):
             assert not torch.equal(p.detach(), b), "optimizer skipped a parameter"
         assert torch.allclose(sink.detach(), before[2] - 0.1 * 0.25)
+
+
+def _worker_direct(rank, world, port, q):
+    """bf16 wire format with DIRECT sinks: the (emulated) wgrad kernel writes bf16 straight into the comm buffer."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    direct = [lin[0].weight, lin[1].weight]
+    flat = FlatGradBuffer(lin.parameters(), device="cpu", comm_dtype=torch.bfloat16, direct_params=direct)
+    assert flat.params[:2] == direct and flat.direct_numel == 32 + 16          # 30 -> 32, 15 -> 16 (16-byte segments)
+    assert all(p._otb_grad.dtype == torch.bfloat16 for p in direct) and lin[0].bias._otb_grad.dtype == torch.float32
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(8, 6, generator=g)
+    lo, hi = shard_batch(8, rank, world)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    ref.load_state_dict(lin.state_dict())
+    ref(X).pow(2).mean().backward()
+    flat.begin_step()
+    shard = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    shard.load_state_dict(lin.state_dict())
+    shard(X[lo:hi]).pow(2).mean().backward()
+    from otter_b200.params import GradSink
+    sink = GradSink()
+    for p, sp in zip(lin.parameters(), shard.parameters()):                    # the "kernels" write through the sinks
+        buf, acc = sink.target(p)
+        assert not acc
+        buf.copy_(sp.grad)
+    flat.finish_step()
+    w = flat.all_reduce(async_op=True)
+    w.wait()
+    ok = all(torch.allclose(p.grad, r.grad, rtol=2e-2, atol=2e-3) for p, r in zip(lin.parameters(), ref.parameters()))
+    second_write_refused = False
+    try:
+        GradSink().target(direct[0])
+    except RuntimeError:
+        second_write_refused = True
+    q.put((rank, ok and second_write_refused, all(p.grad.dtype == torch.float32 for p in lin.parameters()), flat.numel))
+    dist.destroy_process_group()
+
+
+def test_flat_allreduce_world2_bf16_direct_sinks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_direct, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(ok and views for _, ok, views, _ in res), res

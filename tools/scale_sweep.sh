@@ -13,7 +13,7 @@ run() {
   port=$((port + 1))
   echo "=== $name"
   timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 \
-    --master-port "$port" bench.py --gpus "$N" --steps 20 --warmup 5 --no-cpu-baseline "$@" \
+    --master-port "$port" bench.py --gpus "$N" --steps 20 --warmup 5 --no-cpu-baseline --no-extras --no-self-check --no-kernel-rooflines "$@" \
     > "$out/$name.log" 2> "$out/$name.err"
   echo "    exit $?"; grep -h '"metric"' "$out/$name.log" | python -c "
 import sys, json
@@ -23,6 +23,8 @@ for l in sys.stdin:
 NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL run fp32_debug --steps 3
 run fp32
 run bf16 --grad-comm-dtype bf16
+run bf16_direct --grad-comm-dtype bf16-direct
+run bf16_direct_registered --grad-comm-dtype bf16-direct --nccl-registered
 run fp32_registered --nccl-registered
 run bf16_registered --grad-comm-dtype bf16 --nccl-registered
 run fp32_again
