@@ -517,6 +517,90 @@ def fuyu_patch_linear_times(dev):
     return res
 
 
+class _BenchTokenizer:
+    """Offline stand-in for the HF tokenizer the model constructor downloads (no network on the box): ids only."""
+    pad_token = None
+
+    def __init__(self, base=50277):
+        self.vocab, self.base = {}, base
+
+    @classmethod
+    def from_pretrained(cls, *a, **k):
+        return cls()
+
+    def add_special_tokens(self, d):
+        for tok in d.get("additional_special_tokens", []):
+            self.vocab.setdefault(tok, self.base + len(self.vocab))
+        if "pad_token" in d:
+            self.pad_token = d["pad_token"]
+            self.vocab.setdefault(d["pad_token"], self.base + len(self.vocab))
+        return len(self.vocab)
+
+    def encode(self, text):
+        return [self.vocab[text]]
+
+    def __len__(self):
+        return self.base + len(self.vocab)
+
+
+def m2_dropin_times(dev, batch, L, steps=5):
+    """Harness mode M2: the full drop-in OtterForConditionalGeneration at the OTTER-Image-MPT7B shape —
+    CLIP ViT-L/14 + perceiver + 32 frozen MPT layers (D 4096, 32 heads, ALiBi) with a gated block before every 4th,
+    tied 50432-token LM head, shifted cross-entropy — through the reference's forward() signature, forward + backward,
+    eager launches (the HF module plumbing is not graph-captured)."""
+    from otter_b200 import otter_hf
+    otter_hf.AutoTokenizer = _BenchTokenizer
+    torch.manual_seed(SEED)
+    text = dict(d_model=4096, n_heads=32, n_layers=32, expansion_ratio=4, max_seq_len=2048, vocab_size=50432, no_bias=True,
+                attn_config=dict(attn_impl="torch", alibi=True, alibi_bias_max=8), architectures=["MPTForCausalLM"],
+                tie_word_embeddings=True, init_device="cpu")
+    vis = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16, image_size=224,
+               patch_size=14, hidden_act="quick_gelu")
+    with torch.device(dev):
+        model = otter_hf.OtterForConditionalGeneration(otter_hf.OtterConfig(vision_config=vis, text_config=text,
+                                                                             cross_attn_every_n_layers=4))
+    with torch.no_grad():
+        for n_, p_ in model.named_parameters():
+            if n_.endswith("attn_gate") or n_.endswith("ff_gate"):
+                p_.fill_(0.5)
+            elif "lang_encoder" in n_ and "gated_cross_attn" not in n_ and p_.dim() == 2:
+                p_.normal_(0.0, 0.02)
+    model.train()
+    g = torch.Generator().manual_seed(SEED)
+    vision_x = torch.randn(batch, 1, 1, 3, 224, 224, generator=g).to(torch.bfloat16).to(dev)
+    lang_x = torch.randint(3, 50000, (batch, L), generator=g).to(dev)
+    lang_x[:, 0] = model.media_token_id
+    labels = lang_x.clone()
+    labels[:, 0] = -100
+    mask = torch.ones_like(lang_x)
+    trainable = [p_ for p_ in model.parameters() if p_.requires_grad]
+
+    def one():
+        for p_ in trainable:
+            p_.grad = None
+        out = model(vision_x=vision_x, lang_x=lang_x, attention_mask=mask, labels=labels)
+        out.loss.backward()
+        return out.loss
+
+    for _ in range(3):
+        loss = one()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    lm_flops = 2 * 32 * 12 * 4096 * 4096 * 2 + 2 * 2 * 50432 * 4096 * 1.5       # per token: fwd + dgrad (+ LM head fwd+dgrad+wgrad)
+    res = {"samples_per_s": round(batch / (ms * 1e-3), 1), "ms_per_step": round(ms, 2), "per_gpu_batch": batch, "L": L,
+           "steps": steps, "loss": round(float(loss), 4), "launch": "eager",
+           "trainable_params": sum(p_.numel() for p_ in trainable),
+           "algorithmic_tflops": round((flops_per_sample(L) + lm_flops * L) * batch / (ms * 1e-3) / 1e12, 1)}
+    del model, trainable
+    return res
+
+
 def run_extras(dev, rank, world, args, log):
     """Other BASELINE.json configurations / sweep points, measured the same way (device-timed, CUDA graphs, W >= 3),
     reported as extra fields: they do not change `value`."""
@@ -550,6 +634,14 @@ def run_extras(dev, rank, world, args, log):
             extras["c5_fuyu_patch_linear"] = fuyu_patch_linear_times(dev)
         except Exception as e:
             extras["c5_fuyu_patch_linear"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        try:
+            from otter_b200 import params as P
+            extras["m2_dropin_otter_mpt7b"] = m2_dropin_times(dev, 8, BASE_CFG["L"])
+            log(f"extra M2 drop-in: {extras['m2_dropin_otter_mpt7b']['ms_per_step']} ms/step")
+            P.clear_caches()
+            torch.cuda.empty_cache()
+        except Exception as e:
+            extras["m2_dropin_otter_mpt7b"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return extras
 
 

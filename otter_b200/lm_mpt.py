@@ -261,9 +261,18 @@ class MPTModel(nn.Module):
         if output_attentions:
             raise NotImplementedError("output_attentions is not implemented for the fused attention kernel")
         if attention_mask is not None:
-            attention_mask = attention_mask.bool()
-            if attention_mask[:, 0].sum() != attention_mask.shape[0] and self.training:    # modeling_mpt.py:203-204
+            # ONE host read per forward for both checks (the reference syncs here too, modeling_mpt.py:203): left
+            # padding in training is the reference's error; interior padding is what the fused causal kernel cannot
+            # express.  A right-padded mask needs no key mask under causality, so the layers get attention_mask=None.
+            am = attention_mask.bool()
+            left_pad = am[:, 0].sum() != am.shape[0]
+            ragged = ~(am[:, 1:] <= am[:, :-1]).all()
+            left_pad, ragged = (bool(v) for v in torch.stack([left_pad, ragged]).tolist())
+            if left_pad and self.training:                                                 # modeling_mpt.py:203-204
                 raise NotImplementedError("MPT does not support training with left padding.")
+            if left_pad or ragged:
+                raise NotImplementedError("otter_b200 MPT: only right-padded batches (no interior / left padding)")
+            attention_mask = None
         S = input_ids.size(1)
         assert S <= self.config.max_seq_len, \
             f"Cannot forward input with seq_len={S}, this model only supports seq_len<={self.config.max_seq_len}"
