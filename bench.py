@@ -980,8 +980,9 @@ def main():
     ap.add_argument("--no-self-check", action="store_true", help="skip the post-timing oracle check at batch 1")
     ap.add_argument("--no-kernel-rooflines", action="store_true", help="skip the HBM-bound kernel timings")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--multi-cast", action="store_true", default=os.environ.get("OTB_MULTI_CAST") == "1",
-                    help="re-derive the bf16 weight copies in one multi-tensor launch")
+    ap.add_argument("--no-multi-cast", dest="multi_cast", action="store_false",
+                    help="re-derive the bf16 weight copies with one cast launch per weight instead of one multi-tensor launch")
+    ap.set_defaults(multi_cast=True)
     ap.add_argument("--grad-comm-dtype", default="fp32", choices=["fp32", "bf16", "bf16-direct"],
                     help="wire format of the single gradient all-reduce (gradients stay fp32 on both sides); bf16 "
                          "halves the payload to SURVEY.md §8e's 2.36 GB at the cost of two cast passes per step")

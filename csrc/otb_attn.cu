@@ -518,14 +518,17 @@ attn_fwd_resident_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 //
 //   warp 0      TMA producer: Q tiles (double-buffered), then every K / V tile once — they stay resident in smem
 //               for all query tiles of this (problem, head), so CLIP reads K/V once instead of once per query tile
-//   warp 1      allocates TMEM; one lane issues every tcgen05.mma:  S_j = Q K_j^T  (N = the tile's key count
-//               rounded up to 16, so a 1-key remainder tile costs one 16-wide MMA instead of a 128-wide one) and
-//               O += P_j V_j (double-buffered O so the next query tile's S overlaps this tile's epilogue)
+//   warp 1      allocates TMEM; one lane issues every tcgen05.mma:  S_j = Q K_j^T for all key tiles of a query tile
+//               (N = the tile's key count rounded up to 16: a 1-key remainder tile costs one 16-wide MMA), then,
+//               once the softmax warps have published P, O = sum_j P_j V_j; O is double-buffered
 //   warps 2-9   softmax + epilogue: warp pair (w, w+4) shares TMEM lane quarter w % 4 (= rows) and splits each key
 //               tile's 16-column chunks even / odd; row max and row sum are exchanged inside the pair through smem
-//               and a 64-thread named barrier.  P tiles (bf16, SW128) are double-buffered.
+//               and a 64-thread named barrier.  Every key tile has its own P buffer (bf16, SW128), so a query tile
+//               needs ONE hand-off to the MMA warp, and the epilogue of tile i is deferred until after the softmax
+//               of tile i+1: the P V latency of tile i and the S latency of tile i+2 hide behind softmax work.
 // Every hand-off is an mbarrier (TMA complete_tx, tcgen05.commit, or one arrive per softmax warp): there is no
-// __syncthreads between the prologue and the teardown.
+// __syncthreads between the prologue and the teardown.  (ncu, CLIP shape, first version with per-key-tile hand-offs:
+// 25 us, most warp samples in mbarrier waits — profiles/r02_ncu_attn.md.)
 // ================================================================================================
 constexpr int kWsThreads = 320;
 __global__ void __launch_bounds__(kWsThreads, 1)
@@ -537,19 +540,18 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint8_t* s_q = smem;                              // 2 x 16 KB
   uint8_t* s_k = s_q + 2 * kTileBytes;              // nt x 16 KB
   uint8_t* s_v = s_k + nt * kTileBytes;             // nt x 16 KB
-  uint8_t* s_p = s_v + nt * kTileBytes;             // 2 x 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 4 * kTileBytes);
+  uint8_t* s_p = s_v + nt * kTileBytes;             // nt x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * nt * kTileBytes);
   uint64_t* bar_q = bars;             // [2] Q tile landed
   uint64_t* bar_qfree = bars + 2;     // [2] S MMAs that read the Q buffer retired
   uint64_t* full_k = bars + 4;        // [3]
   uint64_t* full_v = bars + 7;        // [3]
-  uint64_t* bar_s = bars + 10;        // [3] S_j complete (once per query tile)
-  uint64_t* bar_sfree = bars + 13;    //     softmax finished reading S of this query tile (8 warp arrivals)
-  uint64_t* p_ready = bars + 14;      // [2] P buffer written (8 warp arrivals)
-  uint64_t* bar_pv = bars + 16;       // [2] P V MMA that read the P buffer retired
-  uint64_t* bar_o = bars + 18;        // [2] O buffer complete
-  uint64_t* bar_ofree = bars + 20;    // [2] epilogue finished reading the O buffer (8 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* bar_s = bars + 10;        //     every S_j of this query tile complete
+  uint64_t* bar_sfree = bars + 11;    //     softmax finished reading S of this query tile (8 warp arrivals)
+  uint64_t* p_ready = bars + 12;      //     every P_j of this query tile written (8 warp arrivals)
+  uint64_t* bar_o = bars + 13;        // [2] O buffer complete (= the P V MMAs of that query tile retired)
+  uint64_t* bar_ofree = bars + 15;    // [2] epilogue finished reading the O buffer (8 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   __shared__ float red_m[256];        // [2 column halves][128 rows]
   __shared__ float red_l[256];
 
@@ -562,11 +564,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_q[i], 1); mbar_init(&bar_qfree[i], 1); mbar_init(&p_ready[i], 8); mbar_init(&bar_pv[i], 1);
-      mbar_init(&bar_o[i], 1); mbar_init(&bar_ofree[i], 8);
+      mbar_init(&bar_q[i], 1); mbar_init(&bar_qfree[i], 1); mbar_init(&bar_o[i], 1); mbar_init(&bar_ofree[i], 8);
     }
-    for (int i = 0; i < 3; ++i) { mbar_init(&full_k[i], 1); mbar_init(&full_v[i], 1); mbar_init(&bar_s[i], 1); }
-    mbar_init(bar_sfree, 8);
+    for (int i = 0; i < 3; ++i) { mbar_init(&full_k[i], 1); mbar_init(&full_v[i], 1); }
+    mbar_init(bar_s, 1); mbar_init(bar_sfree, 8); mbar_init(p_ready, 8);
     fence_mbar_init();
     // the loads need no TMEM: start them before the CTA-wide prologue barrier
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_kv1); tma_prefetch_desc(&map_kv2);
@@ -621,24 +622,22 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           const uint64_t db = make_smem_desc(smem_u32(s_k + j * kTileBytes), 16, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + j * 128, da + k * 2, db + k * 2, idesc_s, k != 0);
-          umma_commit(&bar_s[j]);
         }
+        umma_commit(bar_s);
         umma_commit(&bar_qfree[qb]);
-        if (it >= 2) { mbar_wait(&bar_ofree[ob], ((it >> 1) - 1) & 1); tc_fence_after(); }
+        mbar_wait(p_ready, it & 1);
+        if (it >= 2) mbar_wait(&bar_ofree[ob], ((it >> 1) - 1) & 1);
+        tc_fence_after();
         for (int j = 0; j < nt; ++j) {
-          const int g = it * nt + j, b = g & 1;
+          if (it == 0) { mbar_wait(&full_v[j], 0); tc_fence_after(); }
           const KeyTile kt = key_tile(p, prob, j, nt1);
           const int ksteps = (kt.valid + 15) >> 4;
-          mbar_wait(&p_ready[b], (g >> 1) & 1);
-          if (it == 0) mbar_wait(&full_v[j], 0);
-          tc_fence_after();
-          const uint8_t* pbuf = s_p + b * 2 * kTileBytes;
+          const uint8_t* pbuf = s_p + j * 2 * kTileBytes;
           const uint64_t db = make_smem_desc(smem_u32(s_v + j * kTileBytes), 16, 1024);
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t dp = make_smem_desc(smem_u32(pbuf + (k >> 2) * kTileBytes) + (k & 3) * 32, 16, 1024);
             umma_bf16(t_o + ob * 64, dp, db + k * 128, idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
           }
-          umma_commit(&bar_pv[b]);
         }
         umma_commit(&bar_o[ob]);
       }
@@ -650,8 +649,41 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int r_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     pdl_wait();
+
+    // O / l -> bf16 (this warp: 32 of the 64 head columns) + LSE of one finished query tile
+    auto epilogue = [&](int t, int row, bool row_ok, bool active, int cls, float m_run, float l_run) {
+      const int ob = t & 1;
+      if (active) {
+        const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+        uint32_t r[32];
+        tmem_ld32(t_o + ob * 64 + lane_addr + half * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          bf16* dst = p.out + static_cast<long long>(prob * p.Sq + row) * p.ldo + p.o_col0 + h * 64 + half * 32;
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[g4 * 8 + 0]) * inv_l, __uint_as_float(r[g4 * 8 + 1]) * inv_l);
+            o.y = pack_bf16x2(__uint_as_float(r[g4 * 8 + 2]) * inv_l, __uint_as_float(r[g4 * 8 + 3]) * inv_l);
+            o.z = pack_bf16x2(__uint_as_float(r[g4 * 8 + 4]) * inv_l, __uint_as_float(r[g4 * 8 + 5]) * inv_l);
+            o.w = pack_bf16x2(__uint_as_float(r[g4 * 8 + 6]) * inv_l, __uint_as_float(r[g4 * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + g4 * 8) = o;
+          }
+          if (half == 0 && p.lse != nullptr)
+            p.lse[(static_cast<long long>(prob) * p.H + h) * p.Sq + row] =
+                (cls == 1 && l_run > 0.f) ? (m_run * p.scale + logf(l_run)) : 0.f;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ofree[ob]);
+    };
+
+    int p_row = 0, p_cls = 0;                       // the previous query tile, whose epilogue is still owed
+    bool p_row_ok = false, p_active = false;
+    float p_m = 0.f, p_l = 0.f;
     for (int it = 0; it < nq; ++it) {
-      const int qt = qt0 + it, ob = it & 1;
+      const int qt = qt0 + it;
       const int row = qt * 128 + r_in_tile;
       const bool row_ok = row < p.Sq;
       const bool warp_active = (qt * 128 + quarter * 32) < p.Sq;      // warp-uniform
@@ -660,28 +692,30 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const int cls = row_ok ? row_class(p, tt) : 0;
 
       // ---- sweep 1: row max over the resident S tiles ----
+      mbar_wait(bar_s, it & 1);
+      tc_fence_after();
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      for (int j = 0; j < nt; ++j) {
-        mbar_wait(&bar_s[j], it & 1);
-        if (!warp_active) continue;
-        tc_fence_after();
-        const KeyTile kt = key_tile(p, prob, j, nt1);
-        const RowRange rr = row_range(p, cls, tt, kt, row);
-        const int nch = (kt.valid + 15) >> 4;
-        for (int c = half; c < nch; c += 2) {
-          uint32_t r[16];
-          tmem_ld16(tmem + lane_addr + j * 128 + c * 16, r);
-          tmem_ld_wait();
-          if (cls == 1) {
+      if (warp_active) {                            // warp-uniform: tcgen05.ld is a warp-collective instruction
+        for (int j = 0; j < nt; ++j) {
+          const KeyTile kt = key_tile(p, prob, j, nt1);
+          const RowRange rr = row_range(p, cls, tt, kt, row);
+          const int nch = (kt.valid + 15) >> 4;
+          for (int c = half; c < nch; c += 2) {
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_addr + j * 128 + c * 16, r);
+            tmem_ld_wait();
             const int c0 = c * 16;
-            if (c0 >= rr.lo && c0 + 16 <= rr.hi) {
+            if (cls == 1) {                           // zeroed / uniform rows need no maximum
+              if (c0 >= rr.lo && c0 + 16 <= rr.hi) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
-            } else {
+                for (int i = 0; i < 16; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+              } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (c0 + i >= rr.lo && c0 + i < rr.hi) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+                for (int i = 0; i < 16; ++i)
+                  if (c0 + i >= rr.lo && c0 + i < rr.hi) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+              }
             }
+            __syncwarp();
           }
         }
       }
@@ -691,18 +725,18 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         named_bar_sync(1 + quarter, 64);
         m_run = fmaxf(m_run, red_m[(half ^ 1) * 128 + r_in_tile]);
       }
+      // the P V MMAs of the previous query tile retired: the P buffers may be overwritten (and its O is complete)
+      if (it > 0) { mbar_wait(&bar_o[(it - 1) & 1], ((it - 1) >> 1) & 1); tc_fence_after(); }
 
       // ---- sweep 2: P = exp2((S - m) * scale * log2 e) -> smem (bf16), row sums ----
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
       const float mb = (m_run == -INFINITY) ? 0.f : m_run * p.scale_log2;
-      for (int j = 0; j < nt; ++j) {
-        const int g = it * nt + j, b = g & 1;
-        if (g >= 2) mbar_wait(&bar_pv[b], ((g >> 1) - 1) & 1);       // the P V MMA that read this buffer retired
-        if (warp_active) {
+      if (warp_active) {
+        for (int j = 0; j < nt; ++j) {
           const KeyTile kt = key_tile(p, prob, j, nt1);
           const RowRange rr = row_range(p, cls, tt, kt, row);
           const int nch = (kt.valid + 15) >> 4;
-          uint8_t* pbuf = s_p + b * 2 * kTileBytes;
+          uint8_t* pbuf = s_p + j * 2 * kTileBytes;
           for (int c = half; c < nch; c += 2) {
             uint32_t r[16];
             tmem_ld16(tmem + lane_addr + j * 128 + c * 16, r);
@@ -733,15 +767,14 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
               o.z = pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]); o.w = pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]);
               st_sw128(chunk, r_in_tile, (c & 3) * 16 + u * 8, o);
             }
+            __syncwarp();
           }
-          fence_proxy_async_smem();
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[b]);
+        fence_proxy_async_smem();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sfree);                          // S may be overwritten by the next query tile
+      if (lane == 0) { mbar_arrive(p_ready); mbar_arrive(bar_sfree); }   // P published; S may be overwritten
 
       float l_run = (ls[0] + ls[1]) + (ls[2] + ls[3]);
       if (warp_active) {
@@ -749,34 +782,13 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         named_bar_sync(1 + quarter, 64);
         l_run += red_l[(half ^ 1) * 128 + r_in_tile];
       }
-      // ---- epilogue: O / l -> bf16 (this warp: 32 of the 64 head columns), LSE ----
-      mbar_wait(&bar_o[ob], (it >> 1) & 1);
-      tc_fence_after();
-      if (warp_active) {
-        const float inv_l = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-        uint32_t r[32];
-        tmem_ld32(t_o + ob * 64 + lane_addr + half * 32, r);
-        tmem_ld_wait();
-        if (row_ok) {
-          bf16* dst = p.out + static_cast<long long>(prob * p.Sq + row) * p.ldo + p.o_col0 + h * 64 + half * 32;
-#pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(r[g4 * 8 + 0]) * inv_l, __uint_as_float(r[g4 * 8 + 1]) * inv_l);
-            o.y = pack_bf16x2(__uint_as_float(r[g4 * 8 + 2]) * inv_l, __uint_as_float(r[g4 * 8 + 3]) * inv_l);
-            o.z = pack_bf16x2(__uint_as_float(r[g4 * 8 + 4]) * inv_l, __uint_as_float(r[g4 * 8 + 5]) * inv_l);
-            o.w = pack_bf16x2(__uint_as_float(r[g4 * 8 + 6]) * inv_l, __uint_as_float(r[g4 * 8 + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(dst + g4 * 8) = o;
-          }
-          if (half == 0 && p.lse != nullptr)
-            p.lse[(static_cast<long long>(prob) * p.H + h) * p.Sq + row] =
-                (cls == 1 && l_run > 0.f) ? (m_run * p.scale + logf(l_run)) : 0.f;
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_ofree[ob]);
+      // ---- deferred epilogue of the previous query tile (its O was complete before sweep 2 started) ----
+      if (it > 0) epilogue(it - 1, p_row, p_row_ok, p_active, p_cls, p_m, p_l);
+      p_row = row; p_row_ok = row_ok; p_active = warp_active; p_cls = cls; p_m = m_run; p_l = l_run;
     }
+    mbar_wait(&bar_o[(nq - 1) & 1], ((nq - 1) >> 1) & 1);
+    tc_fence_after();
+    epilogue(nq - 1, p_row, p_row_ok, p_active, p_cls, p_m, p_l);
   }
   tc_fence_before();
   __syncthreads();
@@ -1083,7 +1095,7 @@ extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
   if (rc) return rc;
   OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_kernel, kAttnFwdSmem));
   OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_resident_kernel, (1 + 2 * 3 + 4) * kTileBytes + 1024 + 2048));
-  OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_ws_kernel, (2 + 2 * 3 + 4) * kTileBytes + 1024 + 512));
+  OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_ws_kernel, (2 + 4 * 3) * kTileBytes + 1024 + 512));
   dim3 grid((d->Sq + 127) / 128, d->H, d->P);
   const int nt = (d->Sk1 + 127) / 128 + (d->Sk2 + 127) / 128;
   // OTB_ATTN_WS=0 selects the round-1 resident kernel (kept for A/B measurements)
@@ -1093,7 +1105,7 @@ extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
     // (CLIP: 8 images x 16 heads = 128 CTAs, one wave); otherwise one query tile per CTA for more parallelism
     const int nqt = (d->Sq + 127) / 128;
     const int nq_per_cta = (d->P * d->H >= (sm_count() * 4) / 5) ? nqt : 1;
-    const int smem = (2 + 2 * nt + 4) * kTileBytes + 1024 + 512;
+    const int smem = (2 + 4 * nt) * kTileBytes + 1024 + 512;   // Q x2, K/V resident, one 32 KB P buffer per key tile
     const int tmem_cols = (nt == 1) ? 256 : 512;            // nt x 128 (S) + 2 x 64 (O)
     dim3 g((nqt + nq_per_cta - 1) / nq_per_cta, d->H, d->P);
     OTB_CHECK_CUDA(launch_k(attn_fwd_ws_kernel, g, dim3(kWsThreads), smem, static_cast<cudaStream_t>(stream), mq, mk1,

@@ -731,8 +731,9 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   ep.alpha = e->alpha;
   ep.res_fp32 = e->res_fp32;
   OTB_CHECK_ARG(!e->res_fp32 || e->out_fp32, "otb_gemm_bf16: fp32 residual requires fp32 output");
-  // OTB_GEMM_EPI_TMA=1: bf16 outputs leave through the smem-staged TMA-store epilogue (candidate, off by default)
-  static const bool epi_tma = [] { const char* v = getenv("OTB_GEMM_EPI_TMA"); return v && v[0] == '1'; }();
+  // Outputs leave through the smem-staged TMA-store / reduce-add epilogue (r02: FFN up GELU+aux 194 -> 164 us, fp32
+  // wgrad 206 -> 171 us, step +3 %; profiles/r02_gemm_selftest_bench.md).  OTB_GEMM_EPI_TMA=0 selects direct stores.
+  static const bool epi_tma = [] { const char* v = getenv("OTB_GEMM_EPI_TMA"); return !(v && v[0] == '0'); }();
   ep.tma_out = (epi_tma && !e->res_fp32 && (reinterpret_cast<uintptr_t>(e->out) & 15) == 0 &&
                 (!e->out_fp32 || e->ld_out % 4 == 0)) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -692,7 +692,7 @@ extern "C" int otb_layernorm_fwd(const void* x, int64_t ldx, const float* gamma,
 }
 
 static bool ln_fused_enabled() {
-  static const bool on = [] { const char* e = getenv("OTB_LN_FUSED"); return e && e[0] == '1'; }();
+  static const bool on = [] { const char* e = getenv("OTB_LN_FUSED"); return !(e && e[0] == '0'); }();   // default on
   return on;
 }
 static int ln_fused_grid(int rows) {

@@ -227,7 +227,10 @@ int main(int argc, char** argv) {
       {200, 136, 200, 1, 1, 6},  {1000, 1032, 128, 0, 0, 7},  {2056, 1024, 256, 0, 0, 7}, {520, 4136, 128, 0, 1, 6},
       {300, 40, 64, 0, 0, 7},    {2056, 3072, 128, 0, 0, 5},
   };
-  for (const Case& c : cases) fails += run_case(c);
+  bool no_cases = false;
+  for (int i = 1; i < argc; ++i) no_cases |= (strcmp(argv[i], "--no-cases") == 0);   // profiling runs: only --shape / --bench
+  if (!no_cases)
+    for (const Case& c : cases) fails += run_case(c);
   if (argc > 1 && strcmp(argv[1], "--bench") == 0) {
     bench(2048, 16384, 4096, 0, 0, 1, "gated ffn up (gelu+aux)");
     bench(2048, 4096, 16384, 0, 0, 0, "gated ffn down");

@@ -51,7 +51,7 @@ def _llama_cfg(g, cfg_cls, **kw):
 
 
 def _check(model, out, g, what, loss_tol=2e-2):
-    from tests.test_modules_gpu import check_grads, check_out
+    from test_modules_gpu import check_grads, check_out
     assert abs(out.loss.item() - g["loss"].item()) <= loss_tol * abs(g["loss"].item()), (what, out.loss.item(), g["loss"].item())
     if "logits" in g:
         check_out(out.logits, g["logits"], f"{what} logits", fro=2e-2, mx=6e-2)

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import preprocess as PP
-from tests.test_data_cpu import SIZES, _img
+from test_data_cpu import SIZES, _img
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

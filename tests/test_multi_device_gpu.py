@@ -10,20 +10,31 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _block_step(dev, seed):
+def _make(dev, seed):
+    """Module + inputs; built on the caller's thread (torch's global RNG is not per-thread)."""
     from otter_b200.modeling_otter import OtterGatedCrossAttentionBlock
     torch.manual_seed(seed)
     gb = OtterGatedCrossAttentionBlock(dim=256, dim_visual=128).to(dev)
     with torch.no_grad():
         gb.attn_gate.fill_(0.5), gb.ff_gate.fill_(0.5)
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(2, 40, 256, generator=g).to(dev).requires_grad_(True)
+    x = torch.randn(2, 40, 256, generator=g).to(dev)
     media = torch.randn(2, 1, 64, 128, generator=g).to(dev)
     loc = torch.zeros(2, 40, dtype=torch.bool, device=dev)
     loc[:, 0] = True
+    return gb, x, media, loc
+
+
+def _run(gb, x, media, loc):
+    gb.zero_grad()
+    x = x.detach().clone().requires_grad_(True)
     y = gb(x, media, media_locations=loc)
     y.float().pow(2).mean().backward()
-    return y.detach().float().cpu(), x.grad.float().cpu()
+    return y.detach().float().cpu(), x.grad.float().cpu(), gb.feed_forward[1].weight.grad.float().cpu()
+
+
+def _block_step(dev, seed):
+    return _run(*_make(dev, seed))[:2]
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
@@ -46,15 +57,18 @@ def test_concurrent_threads_on_their_own_streams():
     """Two Python threads, each on its own CUDA stream, running forward+backward concurrently (ctypes releases the GIL):
     results equal the single-threaded run bit for bit; the descriptor cache sees hits."""
     from otter_b200 import _lib
-    want = [_block_step("cuda:0", s) for s in (5, 6)]
+    jobs = [_make("cuda:0", s) for s in (5, 6)]
+    want = [_run(*j) for j in jobs]
+    torch.cuda.synchronize()
     got, errs = [None, None], []
 
     def work(i):
         try:
             st = torch.cuda.Stream(device="cuda:0")
+            st.wait_stream(torch.cuda.default_stream())
             with torch.cuda.stream(st):
                 for _ in range(4):
-                    got[i] = _block_step("cuda:0", 5 + i)
+                    got[i] = _run(*jobs[i])
                 st.synchronize()
         except Exception as e:                              # surfaced below
             errs.append(e)
@@ -63,7 +77,7 @@ def test_concurrent_threads_on_their_own_streams():
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs, errs
-    for (y, g), (yw, gw) in zip(got, want):
-        assert torch.equal(y, yw) and torch.equal(g, gw)
+    for a, b in zip(got, want):
+        assert all(torch.equal(u, v) for u, v in zip(a, b))
     lib = _lib.load()
     assert lib.otb_tmap_cache_stat(0) > 0 and lib.otb_tmap_cache_stat(1) > 0
