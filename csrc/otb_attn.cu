@@ -1098,8 +1098,9 @@ extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
   OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_ws_kernel, (2 + 4 * 3) * kTileBytes + 1024 + 512));
   dim3 grid((d->Sq + 127) / 128, d->H, d->P);
   const int nt = (d->Sk1 + 127) / 128 + (d->Sk2 + 127) / 128;
-  // OTB_ATTN_WS=0 selects the round-1 resident kernel (kept for A/B measurements)
-  static const bool ws_on = [] { const char* v = getenv("OTB_ATTN_WS"); return !(v && v[0] == '0'); }();
+  // OTB_ATTN_WS=1 selects the warp-specialised kernel (v2 is awaiting its GPU validation; the round-1 resident kernel
+  // stays the default until then)
+  static const bool ws_on = [] { const char* v = getenv("OTB_ATTN_WS"); return v && v[0] == '1'; }();
   if (nt <= 3 && ws_on) {
     // one CTA keeps K/V resident for ALL query tiles of its (problem, head) when that already fills the chip
     // (CLIP: 8 images x 16 heads = 128 CTAs, one wave); otherwise one query tile per CTA for more parallelism

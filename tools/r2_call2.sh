@@ -5,6 +5,7 @@ set -u
 out=gpurun_out/r2c2
 mkdir -p "$out"
 python -c "import __graft_entry__ as g; g.build()" > "$out/build.log" 2>&1 || { echo "build failed"; tail -5 "$out/build.log"; exit 1; }
+export OTB_ATTN_WS=1      # validate the warp-specialised attention forward v2 (library default: off until validated)
 run() {
   local name=$1; shift
   local envs=()
