@@ -121,6 +121,25 @@ def refresh(params):
         _shadow[id(p)] = (p._version, t.data_ptr(), out, ref)
 
 
+def install_optimizer_hook(optimizer, params=None):
+    """Re-derive the bf16 compute copies after every `optimizer.step()`.
+
+    The caches above are keyed on `(data_ptr, _version)`.  In-place updates through the public API bump `_version`
+    (torch optimizers, `load_state_dict`), but updates made through `.data` do not — `p.data.copy_()`, DeepSpeed's fp32
+    flat-partition updates (ZeRO 1/2, which the reference's accelerate configs use), EMA swaps — and the kernels would
+    keep computing with stale bf16 weights.  This registers a step post-hook that invalidates the shadows of `params`
+    (default: every parameter of the optimizer's groups); returns the hook handle."""
+    if params is None:
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+    params = list(params)
+
+    def _hook(opt, args, kwargs):
+        invalidate(params)
+        _f32.clear()
+
+    return optimizer.register_step_post_hook(_hook)
+
+
 def clear_caches():
     _shadow.clear()
     _f32.clear()

@@ -107,3 +107,20 @@ def test_dimension_requirements_fail_loudly():
         OtterPerceiverBlock(dim=128, dim_head=32)
     with pytest.raises(NotImplementedError):
         OtterMaskedCrossAttention(dim=64, dim_visual=64, only_attend_immediate_media=False)
+
+
+def test_optimizer_hook_invalidates_shadows_after_data_updates():
+    """ADVICE r1 (params.py): `.data` updates do not bump `_version`; the optimizer post-hook must drop the shadows."""
+    import torch
+    from otter_b200 import params as P
+    w = torch.nn.Parameter(torch.randn(8, 8))
+    opt = torch.optim.SGD([w], lr=0.1)
+    handle = P.install_optimizer_hook(opt)
+    P._shadow[id(w)] = (w._version, w.data_ptr(), torch.zeros(8, 8, dtype=torch.bfloat16), P._ref(P._shadow, w))
+    w.grad = torch.ones_like(w)
+    w.data.add_(1.0)                    # invisible to the version counter
+    assert P._lookup(P._shadow, w, w._version, w.data_ptr())[1] is not None      # still "valid": the stale-cache hazard
+    opt.step()
+    assert P._lookup(P._shadow, w, w._version, w.data_ptr())[1] is None          # invalidated by the hook
+    handle.remove()
+    P.clear_caches()
