@@ -131,6 +131,17 @@ int otb_attn_fwd(const otb_attn_desc* d, void* stream);
 int otb_attn_bwd(const otb_attn_desc* d, const otb_attn_grads* g, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The north star's single fused kernel (SURVEY.md 7 option (a)): masked cross-attention core + to_out projection +
+ * tanh gate + residual, modeling_otter.py:290-340 and :380-389:
+ *     y = ( softmax(mask(q k^T * scale)) v  Wo^T ) * tanh(*gate) + residual
+ * d: the attention problem as for otb_attn_fwd (one key source, Sk1 = T_img * n <= 64, H <= 8 heads of 64); d->out
+ * [P*Sq][H*64] and d->lse still receive O and the log-sum-exp (the backward pass reads them).  wo: bf16 [D][H*64] (the
+ * nn.Linear weight, row pitch ld_wo); aux (optional): bf16 [P*Sq][D] pre-gate branch output O Wo^T (for the gate
+ * gradient); y: bf16 [P*Sq][D].  D must be a multiple of 512. */
+int otb_xattn_out_fused(const otb_attn_desc* d, const void* wo, int64_t ld_wo, const float* gate, const void* residual,
+                        int64_t ld_res, void* aux, int64_t ld_aux, void* y, int64_t ld_y, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * SURVEY.md §8f rank 1 — causal self-attention of the frozen LM decoder layers (head_dim 128: MPT-7B / LLaMA-7B).
  *   mpt/attention.py:22-84 (scaled_multihead_dot_product_attention), :457-464 (ALiBi key bias), :68-75 (causal mask)
  * qkv is the fused Wqkv GEMM output [B*S][qkv_cols] bf16 (row pitch ld_qkv): head h of Q / K / V at columns

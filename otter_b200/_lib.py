@@ -80,6 +80,7 @@ SIGNATURES = {
     "otb_gemm_bf16": (_I, [_VP, _I, _I64, _VP, _I, _I64, _I, _I, _I, C.POINTER(GemmEpilogue), _VP]),
     "otb_attn_fwd": (_I, [C.POINTER(AttnDesc), _VP]),
     "otb_attn_bwd": (_I, [C.POINTER(AttnDesc), C.POINTER(AttnGrads), _VP]),
+    "otb_xattn_out_fused": (_I, [C.POINTER(AttnDesc), _VP, _I64, _VP, _VP, _I64, _VP, _I64, _VP, _I64, _I, _VP]),
     "otb_lm_attn_fwd": (_I, [C.POINTER(LmAttnDesc), _VP]),
     "otb_lm_attn_bwd": (_I, [C.POINTER(LmAttnDesc), C.POINTER(LmAttnGrads), _VP]),
     "otb_text_time": (_I, [_VP, _I, _I, _I, _VP, _VP]),

@@ -17,6 +17,10 @@ BF16 = torch.bfloat16
 # the small ones (projections, perceiver) overlap the latency-bound kernels of the chain instead of serialising with
 # them.  Under CUDA-graph capture the side stream becomes a parallel branch of the graph.  Outputs are allocated on
 # the main stream before the fork and the streams re-join before backward returns.
+import os as _os
+
+# OTB_XATTN_FUSED=1: the gated block's attention + to_out + gate + residual run as ONE kernel (awaiting its GPU validation)
+XATTN_OUT_FUSED = _os.environ.get("OTB_XATTN_FUSED") == "1"
 WGRAD_SIDE_STREAM = False   # measured neutral on B200 (19.28 vs 19.31 ms/step): the large wgrads dominate
 _side = {}
 
@@ -218,6 +222,10 @@ def masked_cross_attention_fwd(x, media, tt, B, L, Tn, n, T_img, heads, norm_w, 
     kv = F.linear_fwd(media, bf16_of(wkv))                                                    # :286-288
     spec = F.AttnSpec(q, 0, kv, 0, inner, B, heads, L, Tn, 0.125, text_time=tt, n_per_media=n, T_img=T_img,
                       mask_ge=mask_ge)
+    if gate is not None and residual is not None and XATTN_OUT_FUSED and F.xattn_out_fusable(spec, wo.shape[0]):
+        # the north star's single kernel: attention + to_out + tanh gate + residual (csrc/otb_xattn_fused.cu)
+        out, a, o, lse = F.xattn_out_fused(spec, bf16_of(wo), f32_of(gate), residual, want_lse=want_lse)
+        return out, (xn, mx, rx, q, kv, o, lse, a)
     o, lse = F.attn_fwd(spec, want_lse=want_lse)                                              # :290-333 fused
     a = None
     if gate is not None:

@@ -306,6 +306,29 @@ def attn_bwd(spec, out, out_col0, lse, dout, dout_col0, dq, dq_col0, dkv1, dk1_c
     return dq, dkv1, dkv2
 
 
+def xattn_out_fusable(spec, D):
+    """The single fused kernel covers the training layout: one key source with T_img * n <= 64 keys, <= 8 heads."""
+    return spec.kv2 is None and spec.Sk1 <= 64 and spec.H <= 8 and D % 512 == 0 and not spec.causal
+
+
+@_on_device
+def xattn_out_fused(spec, wo, gate, residual, want_aux=True, want_lse=True):
+    """-> (y, aux, o, lse): y = (attn(spec) @ wo^T) * tanh(gate) + residual in ONE kernel (otb_xattn_out_fused)."""
+    wo, residual = _mat(wo, "wo"), _mat(residual, "residual")
+    D = wo.shape[0]
+    rows = spec.P * spec.Sq
+    assert wo.shape[1] == spec.H * 64 and residual.shape == (rows, D)
+    o = torch.empty((rows, spec.H * 64), device=wo.device, dtype=BF16)
+    lse = torch.empty((spec.P, spec.H, spec.Sq), device=wo.device, dtype=torch.float32) if want_lse else None
+    y = torch.empty((rows, D), device=wo.device, dtype=BF16)
+    aux = torch.empty((rows, D), device=wo.device, dtype=BF16) if want_aux else None
+    d = spec.desc(o, 0, lse)
+    check(_lib.load().otb_xattn_out_fused(C.byref(d), _p(wo), wo.stride(0), _p(_req(gate, torch.float32, "gate")),
+                                          _p(residual), residual.stride(0), _p(aux), aux.stride(0) if aux is not None else D,
+                                          _p(y), y.stride(0), D, _stream()), "otb_xattn_out_fused")
+    return y, aux, o, lse
+
+
 @_on_device
 def text_time(media_locations, attend_previous=True):
     """bool/uint8 [B,L] -> int32 [B,L]  (bit-exact restatement of modeling_otter.py:298-311)."""

@@ -22,7 +22,8 @@ run pytest_persimmon -- python -m pytest tests/test_persimmon_gpu.py -m gpu -q
 run pytest_callers -- python -m pytest tests/test_callers_gpu.py -m gpu -q
 run pytest_data -- python -m pytest tests/test_data_gpu.py -m gpu -q
 run pytest_multidev -- python -m pytest tests/test_multi_device_gpu.py -m gpu -q
-TMO=900 run pytest_rest -- python -m pytest tests -m gpu -q --ignore tests/test_persimmon_gpu.py --ignore tests/test_callers_gpu.py --ignore tests/test_data_gpu.py --ignore tests/test_multi_device_gpu.py
+run pytest_xfused -- python -m pytest tests/test_xattn_fused_gpu.py -m gpu -q
+TMO=900 run pytest_rest -- python -m pytest tests -m gpu -q --ignore tests/test_persimmon_gpu.py --ignore tests/test_callers_gpu.py --ignore tests/test_data_gpu.py --ignore tests/test_multi_device_gpu.py --ignore tests/test_xattn_fused_gpu.py
 run attn_times -- python tools/prof_attn2.py --time
 OTB_ATTN_WS=0 run attn_times_old -- python tools/prof_attn2.py --time
 TMO=900 run bench_full -- python bench.py --steps 20 --warmup 5
