@@ -42,7 +42,9 @@ def test_fused_kernel_matches_two_kernel_path(B, L, D, n, locs):
     a_ref = torch.empty(B * L, D, device=DEV, dtype=BF16)
     y_ref = F.linear_fwd(o_ref, wo, aux_out=a_ref, scale_ptr=gate, scale_tanh=True, residual=x)
     y, a, o, lse = F.xattn_out_fused(spec, wo, gate, x)
-    assert torch.equal(o, o_ref), (o.float() - o_ref.float()).abs().max().item()          # same kernel arithmetic
+    # same arithmetic up to the summation order of the softmax denominator: at most one bf16 ulp apart
+    assert (o.float() - o_ref.float()).abs().max().item() <= 2.0 ** -7 * o_ref.float().abs().max().item()
+    assert _rel(o, o_ref) <= 2e-3
     assert torch.allclose(lse, lse_ref, rtol=1e-5, atol=1e-5)
     assert (a.float() - a_ref.float()).abs().max().item() <= 2e-2 * a_ref.float().abs().max().item() + 1e-3
     assert _rel(a, a_ref) <= 2e-3 and _rel(y, y_ref) <= 2e-3
