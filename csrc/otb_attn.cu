@@ -471,8 +471,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint64_t* bar_o = bars + 13;        // [2] O buffer complete (= the P V MMAs of that query tile retired)
   uint64_t* bar_ofree = bars + 15;    // [2] epilogue finished reading the O buffer (8 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
-  __shared__ float red_m[256];        // [2 column halves][128 rows]
-  __shared__ float red_l[256];
+  // row max / row sum exchange of a warp pair, [2 column halves][128 rows]; dynamic: static + dynamic smem share the
+  // 227 KB limit and the resident tiles take 224 KB of it
+  float* red = reinterpret_cast<float*>(bars + 18);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.y, prob = blockIdx.z;
@@ -640,9 +641,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       }
       float m_run = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       if (warp_active) {
-        red_m[half * 128 + r_in_tile] = m_run;
+        red[half * 128 + r_in_tile] = m_run;
         named_bar_sync(1 + quarter, 64);
-        m_run = fmaxf(m_run, red_m[(half ^ 1) * 128 + r_in_tile]);
+        m_run = fmaxf(m_run, red[(half ^ 1) * 128 + r_in_tile]);
       }
       // the P V MMAs of the previous query tile retired: the P buffers may be overwritten (and its O is complete)
       if (it > 0) { mbar_wait(&bar_o[(it - 1) & 1], ((it - 1) >> 1) & 1); tc_fence_after(); }
@@ -697,9 +698,11 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 
       float l_run = (ls[0] + ls[1]) + (ls[2] + ls[3]);
       if (warp_active) {
-        red_l[half * 128 + r_in_tile] = l_run;
+        named_bar_sync(1 + quarter, 64);              // both warps of the pair have read the row maxima
+        red[half * 128 + r_in_tile] = l_run;
         named_bar_sync(1 + quarter, 64);
-        l_run += red_l[(half ^ 1) * 128 + r_in_tile];
+        l_run += red[(half ^ 1) * 128 + r_in_tile];
+        named_bar_sync(1 + quarter, 64);              // ... and the row sums, before the next tile's maxima land
       }
       // ---- deferred epilogue of the previous query tile (its O was complete before sweep 2 started) ----
       if (it > 0) epilogue(it - 1, p_row, p_row_ok, p_active, p_cls, p_m, p_l);
@@ -1012,9 +1015,6 @@ extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
   if (d->Sk2 > 0) rc = make_tmap_bf16_2d(&mk2, d->kv2, (uint64_t)d->P * d->Sk2, d->kv2_cols, d->ldkv2, 128, 64);
   else mk2 = mk1;
   if (rc) return rc;
-  OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_kernel, kAttnFwdSmem));
-  OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_resident_kernel, (1 + 2 * 3 + 4) * kTileBytes + 1024 + 2048));
-  OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_ws_kernel, (2 + 4 * 3) * kTileBytes + 1024 + 512));
   dim3 grid((d->Sq + 127) / 128, d->H, d->P);
   const int nt = (d->Sk1 + 127) / 128 + (d->Sk2 + 127) / 128;
   // OTB_ATTN_WS=1 selects the warp-specialised kernel (v2 is awaiting its GPU validation; the round-1 resident kernel
@@ -1025,17 +1025,22 @@ extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
     // (CLIP: 8 images x 16 heads = 128 CTAs, one wave); otherwise one query tile per CTA for more parallelism
     const int nqt = (d->Sq + 127) / 128;
     const int nq_per_cta = (d->P * d->H >= (sm_count() * 4) / 5) ? nqt : 1;
-    const int smem = (2 + 4 * nt) * kTileBytes + 1024 + 512;   // Q x2, K/V resident, one 32 KB P buffer per key tile
+    // Q x2, K/V resident, one 32 KB P buffer per key tile, + alignment slack + barriers and the 1 KB exchange array
+    // (nt = 3: 231,680 of the 232,448 bytes a CTA may have; the kernel declares no static shared memory)
+    const int smem = (2 + 4 * nt) * kTileBytes + 1024 + 1280;
+    OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_ws_kernel, (2 + 4 * 3) * kTileBytes + 1024 + 1280));
     const int tmem_cols = (nt == 1) ? 256 : 512;            // nt x 128 (S) + 2 x 64 (O)
     dim3 g((nqt + nq_per_cta - 1) / nq_per_cta, d->H, d->P);
     OTB_CHECK_CUDA(launch_k(attn_fwd_ws_kernel, g, dim3(kWsThreads), smem, static_cast<cudaStream_t>(stream), mq, mk1,
                             mk2, p, nt, nq_per_cta, tmem_cols));
   } else if (nt <= 3) {
     const int smem = (1 + 2 * nt + 4) * kTileBytes + 1024 + 2048;
+    OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_resident_kernel, (1 + 2 * 3 + 4) * kTileBytes + 1024 + 2048));
     const int tmem_cols = (nt == 1) ? 256 : 512;
     OTB_CHECK_CUDA(launch_k(attn_fwd_resident_kernel, dim3(grid), dim3(kResThreads), smem, static_cast<cudaStream_t>(stream), mq, mk1, mk2, p, nt,
                                                                                              tmem_cols));
   } else {
+    OTB_CHECK_CUDA(ensure_dyn_smem(attn_fwd_kernel, kAttnFwdSmem));
     OTB_CHECK_CUDA(launch_k(attn_fwd_kernel, dim3(grid), dim3(kAttnThreads), kAttnFwdSmem, static_cast<cudaStream_t>(stream), mq, mk1, mk2, p));
   }
   count_launch();

@@ -59,8 +59,7 @@ xattn_out_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   uint64_t* w_free = bars + 15;       // [3]
   uint64_t* y_full = bars + 18;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  __shared__ float red_m[256];
-  __shared__ float red_l[256];
+  float* red = reinterpret_cast<float*>(bars + 21);     // warp-pair exchange [2][128]; dynamic (no static smem: 227 KB limit)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * kXfCols, qt = blockIdx.y, prob = blockIdx.z;
@@ -217,9 +216,9 @@ xattn_out_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       }
       float m_run = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       if (warp_active) {
-        red_m[half * 128 + r_in_tile] = m_run;
+        red[half * 128 + r_in_tile] = m_run;
         named_bar_sync(1 + quarter, 64);
-        m_run = fmaxf(m_run, red_m[(half ^ 1) * 128 + r_in_tile]);
+        m_run = fmaxf(m_run, red[(half ^ 1) * 128 + r_in_tile]);
       }
       if (h > 0) { mbar_wait(&bar_o[(h - 1) & 1], ((h - 1) >> 1) & 1); tc_fence_after(); }   // P V_{h-1} retired
       // ---- sweep 2: P ----
@@ -255,9 +254,11 @@ xattn_out_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       if (lane == 0) { mbar_arrive(p_ready); mbar_arrive(bar_sfree); }
       float l_run = (ls[0] + ls[1]) + (ls[2] + ls[3]);
       if (warp_active) {
-        red_l[half * 128 + r_in_tile] = l_run;
+        named_bar_sync(1 + quarter, 64);              // both warps of the pair have read the row maxima
+        red[half * 128 + r_in_tile] = l_run;
         named_bar_sync(1 + quarter, 64);
-        l_run += red_l[(half ^ 1) * 128 + r_in_tile];
+        l_run += red[(half ^ 1) * 128 + r_in_tile];
+        named_bar_sync(1 + quarter, 64);
       }
       if (h > 0) epilogue(h - 1, p_m, p_l);          // deferred: its O was complete before sweep 2 started
       p_m = m_run; p_l = l_run;
@@ -320,7 +321,7 @@ xattn_out_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   }
 }
 
-constexpr int kXfSmem = 14 * kTileBytes + 1024 + 512;
+constexpr int kXfSmem = 14 * kTileBytes + 1024 + 1280;   // 231,680 of 232,448 bytes; no static shared memory
 
 }  // namespace otb
 
