@@ -42,6 +42,7 @@ struct GemmEpi {
   float alpha;
   int res_fp32;   // residual is fp32 [M][N] (fp32-grade parity path)
   int tma_out;    // bf16 output leaves through a swizzled smem stage + TMA store (full 128 B lines, bounds clipped by TMA)
+  int cls;        // index into kEpiCls when the options match one of the compiled classes, else -1 (run-time options)
 };
 
 template <int BN>
@@ -177,10 +178,44 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpi& ep, float scale, ui
 // fp32 add at L2 (cp.reduce.async.bulk ... add) so the old values never travel to the SM.
 // The stage is reused once the previous bulk operation has finished READING it (wait_group.read), which overlaps
 // with the TMEM load and the math of the next chunk.  The pre-activation side output (aux_out) keeps direct stores.
-template <int BN>
+// CLS >= 0: the epilogue options of launch class kEpiCls[CLS] are compile-time constants — the per-group option tests
+// (uniform branches that cut the 32 independent element streams of a chunk into tiny basic blocks) disappear and the
+// chunk becomes one block the scheduler can interleave.  ncu r02 (profiles/r02_ncu_gemm_epilogue.md): the generic code
+// executes 42 instructions per output for GELU + aux at 0.36 IPC per scheduler with 2 epilogue warps each; 29 % of the
+// stall samples sit on those branches.  CLS = -1: options read from `ep` at run time (any combination).
+struct EpiCls { bool bias, aux_out; int act; bool aux_in, scale, res, out_f32, acc; };
+constexpr int kNumEpiCls = 14;
+constexpr EpiCls kEpiCls[kNumEpiCls] = {
+    /* 0 plain                      */ {false, false, 0, false, false, false, false, false},
+    /* 1 * gate                     */ {false, false, 0, false, true, false, false, false},
+    /* 2 bias                       */ {true, false, 0, false, false, false, false, false},
+    /* 3 bias + quick-GELU          */ {true, false, 2, false, false, false, false, false},
+    /* 4 bias + residual            */ {true, false, 0, false, false, true, false, false},
+    /* 5 residual                   */ {false, false, 0, false, false, true, false, false},
+    /* 6 GELU + pre-activation      */ {false, true, 1, false, false, false, false, false},
+    /* 7 branch out, * gate, + res  */ {false, true, 0, false, true, true, false, false},
+    /* 8 * gelu'(aux) * gate        */ {false, false, 0, true, true, false, false, false},
+    /* 9 * gelu'(aux)               */ {false, false, 0, true, false, false, false, false},
+    /* 10 fp32 store                */ {false, false, 0, false, false, false, true, false},
+    /* 11 fp32 store * gate         */ {false, false, 0, false, true, false, true, false},
+    /* 12 fp32 accumulate           */ {false, false, 0, false, false, false, true, true},
+    /* 13 fp32 accumulate * gate    */ {false, false, 0, false, true, false, true, true},
+};
+
+template <int BN, int CLS>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, float scale, uint32_t taddr, int m0, int n0, int M,
                                                   int N, int q, int half, int lane, uint8_t* stage,
                                                   const CUtensorMap* map_d) {
+  constexpr bool kS = CLS >= 0;
+  constexpr EpiCls kC = kEpiCls[kS ? CLS : 0];
+  const bool f_bias = kS ? kC.bias : (ep.bias != nullptr);
+  const bool f_auxo = kS ? kC.aux_out : (ep.aux_out != nullptr);
+  const int f_act = kS ? kC.act : ep.act;
+  const bool f_auxi = kS ? kC.aux_in : (ep.aux_in != nullptr);
+  const bool f_scale = kS ? kC.scale : true;
+  const bool f_res = kS ? kC.res : (ep.residual != nullptr);
+  const bool f_f32 = kS ? kC.out_f32 : (ep.out_fp32 != 0);
+  const bool f_acc = kS ? kC.acc : (ep.accumulate != 0);
   const int row0 = m0 + q * 32;
   if (row0 >= M) return;                                      // warp-uniform: no row of this quarter is inside
   const int row = row0 + lane;
@@ -195,12 +230,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, float scale
     const bool act_chunk = row_ok;
     uint4 res[4], aux[4];
     if (act_chunk) {
-      if (ep.residual != nullptr) {
+      if (f_res) {
         const uint4* pr = reinterpret_cast<const uint4*>(ep.residual + lrow * ep.ld_res + colbase);
 #pragma unroll
         for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) res[g] = __ldg(pr + g);
       }
-      if (ep.aux_in != nullptr) {
+      if (f_auxi) {
         const uint4* pa = reinterpret_cast<const uint4*>(ep.aux_in + lrow * ep.ld_aux_in + colbase);
 #pragma unroll
         for (int g = 0; g < 4; ++g) if (colbase + g * 8 < N) aux[g] = __ldg(pa + g);
@@ -210,8 +245,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, float scale
     tmem_ld32(taddr + c * 32, r);
     tmem_ld_wait();
     // bf16: two chunks share one 128 B-wide box (units 0-3 / 4-7); fp32: one chunk is one box (units 0-7).
-    const bool first_of_box = ep.out_fp32 || (c & 1) == 0;
-    const bool last_of_box = ep.out_fp32 || (c & 1) == 1 || colbase + 32 >= N;
+    const bool first_of_box = f_f32 || (c & 1) == 0;
+    const bool last_of_box = f_f32 || (c & 1) == 1 || colbase + 32 >= N;
     if (first_of_box) {                                       // the previous box must have left the stage
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
@@ -223,33 +258,33 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, float scale
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
       if (act_chunk && col < N) {
-        if (ep.bias != nullptr) {
+        if (f_bias) {
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
           v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
           v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
-        if (ep.aux_out != nullptr) {
+        if (f_auxo) {
           uint4 x;
           x.x = pack_bf16x2(v[0], v[1]); x.y = pack_bf16x2(v[2], v[3]);
           x.z = pack_bf16x2(v[4], v[5]); x.w = pack_bf16x2(v[6], v[7]);
           *reinterpret_cast<uint4*>(ep.aux_out + lrow * ep.ld_aux_out + col) = x;
         }
-        if (ep.aux_in == nullptr) {
-          if (ep.act == 1) {
+        if (!f_auxi) {
+          if (f_act == 1) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
-          } else if (ep.act == 2) {
+          } else if (f_act == 2) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
-          } else if (ep.act == 3) {                     // relu^2 (Persimmon "relu2")
+          } else if (f_act == 3) {                     // relu^2 (Persimmon "relu2")
 #pragma unroll
             for (int i = 0; i < 8; ++i) { const float r_ = fmaxf(v[i], 0.f); v[i] = r_ * r_; }
           }
         } else {   // backward of the activation whose pre-activation is aux_in: act 3 -> 2 relu(z), otherwise gelu'(z)
           const float2 a0 = unpack_bf16x2(aux[g].x), a1 = unpack_bf16x2(aux[g].y), a2 = unpack_bf16x2(aux[g].z),
                        a3 = unpack_bf16x2(aux[g].w);
-          if (ep.act == 3) {
+          if (f_act == 3) {
             v[0] *= 2.f * fmaxf(a0.x, 0.f); v[1] *= 2.f * fmaxf(a0.y, 0.f);
             v[2] *= 2.f * fmaxf(a1.x, 0.f); v[3] *= 2.f * fmaxf(a1.y, 0.f);
             v[4] *= 2.f * fmaxf(a2.x, 0.f); v[5] *= 2.f * fmaxf(a2.y, 0.f);
@@ -261,9 +296,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, float scale
             v[6] *= gelu_grad_fast(a3.x); v[7] *= gelu_grad_fast(a3.y);
           }
         }
+        if (f_scale) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] *= scale;
-        if (ep.residual != nullptr) {
+          for (int i = 0; i < 8; ++i) v[i] *= scale;
+        }
+        if (f_res) {
           const float2 a0 = unpack_bf16x2(res[g].x), a1 = unpack_bf16x2(res[g].y), a2 = unpack_bf16x2(res[g].z),
                        a3 = unpack_bf16x2(res[g].w);
           v[0] += a0.x; v[1] += a0.y; v[2] += a1.x; v[3] += a1.y;
@@ -271,7 +308,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, float scale
         }
       }
       // rows >= M and columns >= N hold don't-care values: the TMA engine clips them
-      if (ep.out_fp32) {
+      if (f_f32) {
         *reinterpret_cast<float4*>(my_row + (((2 * g) ^ xr) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(my_row + (((2 * g + 1) ^ xr) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
       } else {
@@ -285,13 +322,27 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpi& ep, float scale
       fence_proxy_async_smem();                               // generic-proxy writes -> visible to the TMA engine
       __syncwarp();
       if (lane == 0) {
-        const int box_col = ep.out_fp32 ? colbase : (colbase & ~63);
-        if (ep.accumulate) tma_reduce_add_2d(map_d, stage, box_col, row0);
+        const int box_col = f_f32 ? colbase : (colbase & ~63);
+        if (f_acc) tma_reduce_add_2d(map_d, stage, box_col, row0);
         else tma_store_2d(map_d, stage, box_col, row0);
         tma_store_commit();
       }
     }
   }
+}
+
+// per-tile dispatch on the launch's epilogue class (host: epi_class_of)
+template <int BN>
+__device__ __forceinline__ void epilogue_dispatch_tma(const GemmEpi& ep, float scale, uint32_t taddr, int m0, int n0,
+                                                      int M, int N, int q, int half, int lane, uint8_t* stage,
+                                                      const CUtensorMap* map_d) {
+#define OTB_EPI_CASE(C_) case C_: epilogue_tile_tma<BN, C_>(ep, scale, taddr, m0, n0, M, N, q, half, lane, stage, map_d); break;
+  switch (ep.cls) {
+    OTB_EPI_CASE(0) OTB_EPI_CASE(1) OTB_EPI_CASE(2) OTB_EPI_CASE(3) OTB_EPI_CASE(4) OTB_EPI_CASE(5) OTB_EPI_CASE(6)
+    OTB_EPI_CASE(7) OTB_EPI_CASE(8) OTB_EPI_CASE(9) OTB_EPI_CASE(10) OTB_EPI_CASE(11) OTB_EPI_CASE(12) OTB_EPI_CASE(13)
+    default: epilogue_tile_tma<BN, -1>(ep, scale, taddr, m0, n0, M, N, q, half, lane, stage, map_d); break;
+  }
+#undef OTB_EPI_CASE
 }
 
 // MC = true: clusters of 2 CTAs work on two vertically adjacent 128-row tiles of the same BN-wide column block;
@@ -439,7 +490,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if constexpr (TS)
-        epilogue_tile_tma<BN>(ep, scale, taddr, m0, n0, M, N, q, half, lane, epi_stage + warp * kEpiWarpStage, &map_d);
+        epilogue_dispatch_tma<BN>(ep, scale, taddr, m0, n0, M, N, q, half, lane, epi_stage + warp * kEpiWarpStage, &map_d);
       else
         epilogue_tile<BN>(ep, scale, taddr, m0, n0, M, N, q, half, lane);
       tc_fence_before();
@@ -636,7 +687,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if constexpr (TS)
-        epilogue_tile_tma<BN>(ep, scale, taddr, m0, n0, M, N, q, half, lane, epi_stage + warp * kEpiWarpStage, &map_d);
+        epilogue_dispatch_tma<BN>(ep, scale, taddr, m0, n0, M, N, q, half, lane, epi_stage + warp * kEpiWarpStage, &map_d);
       else
         epilogue_tile<BN>(ep, scale, taddr, m0, n0, M, N, q, half, lane);
       tc_fence_before();
@@ -736,6 +787,21 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   static const bool epi_tma = [] { const char* v = getenv("OTB_GEMM_EPI_TMA"); return !(v && v[0] == '0'); }();
   ep.tma_out = (epi_tma && !e->res_fp32 && (reinterpret_cast<uintptr_t>(e->out) & 15) == 0 &&
                 (!e->out_fp32 || e->ld_out % 4 == 0)) ? 1 : 0;
+  ep.cls = -1;
+  if (ep.tma_out && e->res_fp32 == 0) {
+    const bool scaled = (e->scale_ptr != nullptr) || e->alpha != 1.0f;
+    for (int c = 0; c < kNumEpiCls; ++c) {
+      const EpiCls& k = kEpiCls[c];
+      if (k.bias == (e->bias != nullptr) && k.aux_out == (e->aux_out != nullptr) && k.aux_in == (e->aux_in != nullptr) &&
+          k.act == (e->aux_in ? 0 : e->act) && (e->aux_in == nullptr || e->act != 3) && k.scale == scaled &&
+          k.res == (e->residual != nullptr) && k.out_f32 == (e->out_fp32 != 0) && k.acc == (e->accumulate != 0)) {
+        ep.cls = c;
+        break;
+      }
+    }
+  }
+  static const bool cls_off = [] { const char* v = getenv("OTB_GEMM_EPI_CLS"); return v && v[0] == '0'; }();
+  if (cls_off) ep.cls = -1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // Tile-N choice: 256-wide tiles unless that leaves most SMs idle.  CTA-pair multicast (MC) when there are at

@@ -30,12 +30,15 @@ TMO=900 run bench_full -- python bench.py --steps 20 --warmup 5
 B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras --no-self-check --no-kernel-rooflines"
 run bench_a -- $B
 run bench_noepitma OTB_GEMM_EPI_TMA=0 -- $B
+run bench_noepicls OTB_GEMM_EPI_CLS=0 -- $B
 run bench_nolnfused OTB_LN_FUSED=0 -- $B
 run bench_nomulticast -- $B --no-multi-cast
 run bench_b -- $B
 G="build/selftest_gemm --no-cases --shape 2056 4096 1024 0 0 5 --shape 2056 4096 1024 0 0 0 --shape 2048 16384 64 0 0 0 --shape 2048 16384 64 0 0 1"
 run selftest_shapes -- $G
 run selftest_bench -- build/selftest_gemm --no-cases --bench
+run selftest_bench_nocls OTB_GEMM_EPI_CLS=0 -- build/selftest_gemm --no-cases --bench
+TMO=400 run selftest_cases -- build/selftest_gemm
 for i in 0 1 2 3; do
   TMO=200 run ncu_gemm_epi$i -- ncu --set full --clock-control none --import-source on -k regex:gemm2 -s $((5 + 23 * i)) -c 1 -o "$out/r02_gemm_epi$i" $G
 done
