@@ -620,23 +620,35 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           const KeyTile kt = key_tile(p, prob, j, nt1);
           const RowRange rr = row_range(p, cls, tt, kt, row);
           const int nch = (kt.valid + 15) >> 4;
-          for (int c = half; c < nch; c += 2) {
-            uint32_t r[16];
-            tmem_ld16(tmem + lane_addr + j * 128 + c * 16, r);
-            tmem_ld_wait();
-            const int c0 = c * 16;
-            if (cls == 1) {                           // zeroed / uniform rows need no maximum
-              if (c0 >= rr.lo && c0 + 16 <= rr.hi) {
+          const int my = (nch - half + 1) >> 1;       // this warp's chunks half, half+2, ... (<= 4), warp-uniform
 #pragma unroll
-                for (int i = 0; i < 16; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
-              } else {
+          for (int b2 = 0; b2 < 2; ++b2) {            // two chunks in flight per wait: TMEM round trips were the
+            if (2 * b2 < my) {                        // per-tile cost of the first version
+              uint32_t r[2][16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (c0 + i >= rr.lo && c0 + i < rr.hi) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[i]));
+              for (int u = 0; u < 2; ++u)
+                if (2 * b2 + u < my) tmem_ld16(tmem + lane_addr + j * 128 + (half + 2 * (2 * b2 + u)) * 16, r[u]);
+              tmem_ld_wait();
+              if (cls == 1) {                         // zeroed / uniform rows need no maximum
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  if (2 * b2 + u < my) {
+                    const int c0 = (half + 2 * (2 * b2 + u)) * 16;
+                    if (c0 >= rr.lo && c0 + 16 <= rr.hi) {
+#pragma unroll
+                      for (int i = 0; i < 16; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[u][i]));
+                    } else {
+#pragma unroll
+                      for (int i = 0; i < 16; ++i)
+                        if (c0 + i >= rr.lo && c0 + i < rr.hi) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(r[u][i]));
+                    }
+                  }
+                }
               }
             }
             __syncwarp();
           }
+          __syncwarp();
         }
       }
       float m_run = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
@@ -657,35 +669,46 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           const RowRange rr = row_range(p, cls, tt, kt, row);
           const int nch = (kt.valid + 15) >> 4;
           uint8_t* pbuf = s_p + j * 2 * kTileBytes;
-          for (int c = half; c < nch; c += 2) {
-            uint32_t r[16];
-            tmem_ld16(tmem + lane_addr + j * 128 + c * 16, r);
-            tmem_ld_wait();
-            float pv[16];
-            const int c0 = c * 16;
-            if (cls == 1 && c0 >= rr.lo && c0 + 16 <= rr.hi) {
+          const int my = (nch - half + 1) >> 1;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
-                ls[i & 3] += pv[i];
+          for (int b2 = 0; b2 < 2; ++b2) {
+            if (2 * b2 < my) {
+              uint32_t r[2][16];
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+                if (2 * b2 + u < my) tmem_ld16(tmem + lane_addr + j * 128 + (half + 2 * (2 * b2 + u)) * 16, r[u]);
+              tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                if (2 * b2 + u < my) {
+                  const int c = half + 2 * (2 * b2 + u), c0 = c * 16;
+                  float pv[16];
+                  if (cls == 1 && c0 >= rr.lo && c0 + 16 <= rr.hi) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                      pv[i] = ex2_approx(fmaf(__uint_as_float(r[u][i]), p.scale_log2, -mb));
+                      ls[i & 3] += pv[i];
+                    }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                      float v = 0.f;
+                      if (c0 + i >= rr.lo && c0 + i < rr.hi)
+                        v = (cls == 1) ? ex2_approx(fmaf(__uint_as_float(r[u][i]), p.scale_log2, -mb)) : 1.0f;
+                      pv[i] = v;
+                      ls[i & 3] += v;
+                    }
+                  }
+                  uint8_t* chunk = pbuf + (c >> 2) * kTileBytes;
+#pragma unroll
+                  for (int w2 = 0; w2 < 2; ++w2) {
+                    uint4 o;
+                    o.x = pack_bf16x2(pv[w2 * 8 + 0], pv[w2 * 8 + 1]); o.y = pack_bf16x2(pv[w2 * 8 + 2], pv[w2 * 8 + 3]);
+                    o.z = pack_bf16x2(pv[w2 * 8 + 4], pv[w2 * 8 + 5]); o.w = pack_bf16x2(pv[w2 * 8 + 6], pv[w2 * 8 + 7]);
+                    st_sw128(chunk, r_in_tile, (c & 3) * 16 + w2 * 8, o);
+                  }
+                }
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float v = 0.f;
-                if (c0 + i >= rr.lo && c0 + i < rr.hi)
-                  v = (cls == 1) ? ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb)) : 1.0f;
-                pv[i] = v;
-                ls[i & 3] += v;
-              }
-            }
-            uint8_t* chunk = pbuf + (c >> 2) * kTileBytes;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              uint4 o;
-              o.x = pack_bf16x2(pv[u * 8 + 0], pv[u * 8 + 1]); o.y = pack_bf16x2(pv[u * 8 + 2], pv[u * 8 + 3]);
-              o.z = pack_bf16x2(pv[u * 8 + 4], pv[u * 8 + 5]); o.w = pack_bf16x2(pv[u * 8 + 6], pv[u * 8 + 7]);
-              st_sw128(chunk, r_in_tile, (c & 3) * 16 + u * 8, o);
             }
             __syncwarp();
           }
@@ -1017,9 +1040,9 @@ extern "C" int otb_attn_fwd(const otb_attn_desc* d, void* stream) {
   if (rc) return rc;
   dim3 grid((d->Sq + 127) / 128, d->H, d->P);
   const int nt = (d->Sk1 + 127) / 128 + (d->Sk2 + 127) / 128;
-  // OTB_ATTN_WS=1 selects the warp-specialised kernel (v2 is awaiting its GPU validation; the round-1 resident kernel
-  // stays the default until then)
-  static const bool ws_on = [] { const char* v = getenv("OTB_ATTN_WS"); return v && v[0] == '1'; }();
+  // warp-specialised kernel by default (validated r2c3: 13 kernel + 71 module tests; CLIP 32.5 -> 23.3 us, A 11.1 -> 9.8,
+  // B 7.3 -> 5.5 us in graph replay); OTB_ATTN_WS=0 selects the round-1 resident kernel
+  static const bool ws_on = [] { const char* v = getenv("OTB_ATTN_WS"); return !(v && v[0] == '0'); }();
   if (nt <= 3 && ws_on) {
     // one CTA keeps K/V resident for ALL query tiles of its (problem, head) when that already fills the chip
     // (CLIP: 8 images x 16 heads = 128 CTAs, one wave); otherwise one query tile per CTA for more parallelism
