@@ -811,7 +811,12 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   const bool bn128 = (N <= 128) || (tiles256 < sm_count() && N > 128);
   const int tiles = bn128 ? tiles_m * ((N + 127) / 128) : tiles256;
   static const bool mc_off = (getenv("OTB_GEMM_NO_MCAST") != nullptr);
-  const bool mc = !mc_off && tiles_m >= 2 && (tiles_m % 2 == 0 || tiles_m >= 9) && tiles >= sm_count();
+  // OTB_GEMM_MC_MIN_TILES: smallest tile count that uses the 2-CTA multicast variant (default: one tile per SM).  CLIP
+  // out_proj / fc2 (136 tiles of 128x128, K up to 4096) are L2-bandwidth bound at 64 FLOP/B; sharing the B tile in a
+  // pair cuts their L2 traffic by a quarter.
+  static const int mc_min_tiles = [] { const char* v = getenv("OTB_GEMM_MC_MIN_TILES"); return v ? atoi(v) : 0; }();
+  const bool mc = !mc_off && tiles_m >= 2 && (tiles_m % 2 == 0 || tiles_m >= 9) &&
+                  tiles >= (mc_min_tiles > 0 ? mc_min_tiles : sm_count());
   const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   // cta_group::2 pair kernel for the large problems (>= one 256x256 pair tile per SM pair)
   static const int two_cta = [] { const char* e = getenv("OTB_GEMM_2CTA"); return e ? atoi(e) : 1; }();

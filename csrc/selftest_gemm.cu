@@ -231,7 +231,9 @@ int main(int argc, char** argv) {
   for (int i = 1; i < argc; ++i) no_cases |= (strcmp(argv[i], "--no-cases") == 0);   // profiling runs: only --shape / --bench
   if (!no_cases)
     for (const Case& c : cases) fails += run_case(c);
-  if (argc > 1 && strcmp(argv[1], "--bench") == 0) {
+  bool do_bench = false;
+  for (int i = 1; i < argc; ++i) do_bench |= (strcmp(argv[i], "--bench") == 0);
+  if (do_bench) {
     bench(2048, 16384, 4096, 0, 0, 1, "gated ffn up (gelu+aux)");
     bench(2048, 4096, 16384, 0, 0, 0, "gated ffn down");
     bench(2048, 16384, 4096, 0, 1, 0, "dgrad via MN-major W");
