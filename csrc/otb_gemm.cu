@@ -820,10 +820,9 @@ extern "C" int otb_gemm_bf16(const void* A, int a_mn_major, int64_t lda, const v
   const int sel = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   // cta_group::2 pair kernel for the large problems (>= one 256x256 pair tile per SM pair)
   static const int two_cta = [] { const char* e = getenv("OTB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
-  // OTB_GEMM2_MIN_PAIRS: smallest number of 256x256 pair tiles that goes to the pair kernel (default: one per SM pair)
-  static const int min_pairs = [] { const char* v = getenv("OTB_GEMM2_MIN_PAIRS"); return v ? atoi(v) : 0; }();
+  // (sending the 36-pair-tile CLIP out_proj / fc2 problems to the pair kernel was measured slower: profiles/r02_call1_knob_ab.md)
   const int pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
-  const bool pair_ok = min_pairs > 0 ? (pair_tiles >= min_pairs && N >= 256 && M > 128) : (!bn128 && pair_tiles >= sm_count() / 2);
+  const bool pair_ok = !bn128 && pair_tiles >= sm_count() / 2;
   if (two_cta && pair_ok) {
 #define OTB_GEMM2_CASE(A_, B_)                                                        \
   return ep.tma_out ? launch_gemm2<A_, B_, true>(A, lda, B, ldb, M, N, K, ep, st)     \
