@@ -151,9 +151,13 @@ class HotPath:
         self.cfg, self.batch, self.dev, self.rank, self.world, self.args = cfg, batch, dev, rank, world, args
         self.clip, self.perceiver, self.gated = build_modules(dev, cfg)
         self.trainable = list(self.perceiver.parameters()) + list(self.gated.parameters())
-        comm_dtype = torch.bfloat16 if args.grad_comm_dtype.startswith("bf16") else None
+        mode = args.grad_comm_dtype
+        if mode == "auto":       # measured at N = 2 (profiles/r02_scale_sweep_n2.md): bf16-direct 713, fp32 688-705, bf16 664
+            mode = "bf16-direct" if world > 1 else "fp32"
+        self.comm_mode = mode
+        comm_dtype = torch.bfloat16 if mode.startswith("bf16") else None
         direct = None
-        if args.grad_comm_dtype == "bf16-direct":      # the Linear weights' wgrad epilogues write the wire buffer
+        if mode == "bf16-direct":                      # the Linear weights' wgrad epilogues write the wire buffer
             direct = [m.weight for mod in (self.perceiver, self.gated) for m in mod.modules()
                       if isinstance(m, torch.nn.Linear)]
         self.flat = FlatGradBuffer(self.trainable, device=dev, comm_dtype=comm_dtype,
@@ -732,6 +736,7 @@ def run_cuda(args):
         except Exception as e:
             check = {"ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
     h2d = hp.h2d_bytes()
+    comm_mode = hp.comm_mode
     comm_bytes = hp.flat.comm_nbytes() if world > 1 else 0
     hp.close()
     del hp
@@ -767,10 +772,12 @@ def run_cuda(args):
                    "launch": "eager" if args.no_graph else "two CUDA graphs per step (frozen CLIP forward | perceiver + gated "
                              "fwd/bwd), replayed" + ("; the single NCCL gradient all-reduce runs between them, overlapped "
                              "with the CLIP forward of the next batch" if world > 1 else ""),
-                   "weights": "fp32 master, bf16 compute copies re-cast every step; fp32 grads in one flat buffer",
+                   "weights": "fp32 master, bf16 compute copies re-cast every step; fp32 `.grad` views of one flat buffer" +
+                              ("; the Linear weights' wgrad epilogues write the bf16 wire buffer of the all-reduce, one up-cast "
+                               "after it" if comm_mode == "bf16-direct" else ""),
                    "cache": "per-step working set (2.4 GB bf16 weights + activations) >> 126 MB L2; no explicit flush",
                    "grad_allreduce_bytes": comm_bytes,
-                   "grad_allreduce_dtype": args.grad_comm_dtype, "nccl_registered_buffer": bool(args.nccl_registered)},
+                   "grad_allreduce_dtype": comm_mode, "nccl_registered_buffer": bool(args.nccl_registered)},
         "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "h2d_overlapped_with_previous_step": bool(args.e2e_prefetch)},
@@ -983,9 +990,10 @@ def main():
     ap.add_argument("--no-multi-cast", dest="multi_cast", action="store_false",
                     help="re-derive the bf16 weight copies with one cast launch per weight instead of one multi-tensor launch")
     ap.set_defaults(multi_cast=True)
-    ap.add_argument("--grad-comm-dtype", default="fp32", choices=["fp32", "bf16", "bf16-direct"],
-                    help="wire format of the single gradient all-reduce (gradients stay fp32 on both sides); bf16 "
-                         "halves the payload to SURVEY.md §8e's 2.36 GB at the cost of two cast passes per step")
+    ap.add_argument("--grad-comm-dtype", default="auto", choices=["auto", "fp32", "bf16", "bf16-direct"],
+                    help="wire format of the single gradient all-reduce (`.grad` is fp32 either way).  bf16 halves the "
+                         "payload to SURVEY.md §8e's 2.36 GB at the cost of two cast passes; bf16-direct lets the wgrad "
+                         "epilogues write the wire buffer (one up-cast after the collective).  auto = bf16-direct for N > 1")
     ap.add_argument("--e2e-prefetch", action="store_true",
                     help="e2e leg: copy the next step's inputs host->device on a copy stream while this step computes")
     ap.add_argument("--nccl-registered", action="store_true",

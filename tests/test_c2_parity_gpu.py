@@ -166,3 +166,41 @@ def test_gate_grad_and_layernorm_bwd_at_step_shapes(rows, D):
     torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-5).backward(dy.float())
     _close(dx, xr.grad + add.float(), 1e-2, 2e-2, "ln dx + add")
     assert _rel(dgam, gr.grad) <= 2e-3 and _rel(dbet, br.grad) <= 2e-3, (_rel(dgam, gr.grad), _rel(dbet, br.grad))
+
+
+def test_direct_wire_format_sinks_match_fp32_sinks():
+    """FlatGradBuffer(direct_params=...): the wgrad epilogues write bf16 straight into the all-reduce's wire buffer
+    (the N > 1 default of bench.py).  Single rank: after all_reduce() the fp32 `.grad` views must equal the fp32-sink
+    gradients up to one bf16 rounding (rel-Frobenius <= 4e-3), and a second write in the same step is refused."""
+    from otter_b200.dp import FlatGradBuffer
+    from otter_b200.modeling_otter import OtterGatedCrossAttentionBlock
+    B, L, D, Dv, n = 2, 128, 1024, 256, 64
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, L, D, generator=g).to(BF16).to(DEV)
+    media = torch.randn(B, 1, n, Dv, generator=g).to(BF16).to(DEV)
+    w = torch.randn(B, L, D, generator=g).to(BF16).to(DEV)
+    loc = torch.zeros(B, L, dtype=torch.bool, device=DEV)
+    loc[:, 0] = True
+    grads = {}
+    for mode in ("fp32", "direct"):
+        torch.manual_seed(4)
+        gb = OtterGatedCrossAttentionBlock(dim=D, dim_visual=Dv).to(DEV)
+        with torch.no_grad():
+            gb.attn_gate.fill_(0.5), gb.ff_gate.fill_(0.5)
+        params = list(gb.parameters())
+        direct = [m.weight for m in gb.modules() if isinstance(m, torch.nn.Linear)] if mode == "direct" else None
+        flat = FlatGradBuffer(params, device=DEV, comm_dtype=torch.bfloat16 if direct else None, direct_params=direct)
+        for _ in range(2):                                  # second step: the sinks are reused
+            flat.begin_step()
+            y = gb(x.clone().requires_grad_(True), media, media_locations=loc)
+            (y.float() * w).sum().backward()
+            flat.finish_step()
+            flat.all_reduce()
+        torch.cuda.synchronize()
+        grads[mode] = {k: p.grad.detach().float().clone() for k, p in gb.named_parameters()}
+        if direct:
+            assert all(p._otb_grad.dtype == BF16 for p in direct)
+    for k, ref in grads["fp32"].items():
+        got = grads["direct"][k]
+        tol = 4e-3 if ref.dim() == 2 else 1e-6
+        assert _rel(got, ref) <= tol, (k, _rel(got, ref))
