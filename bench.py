@@ -788,9 +788,10 @@ def run_cuda(args):
                                "(fwd, dgrad, wgrad) of the gated blocks, 48 launches/step",
                      "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": round(ach / peak_tf, 4) if peak_tf else None,
-                     "traffic": 269.4e6, "traffic_note": "dram read+write of one 2048x16384x4096 GELU+aux launch of "
-                                                         "gemm2_bf16_kernel, ncu --set full, profiles/r01_ncu_full_v2.md "
-                                                         "(algorithmic 285 MB)",
+                     "traffic": 259.1e6, "traffic_note": "dram read+write of one 2048x16384x4096 GELU+aux launch of "
+                                                         "gemm2_bf16_kernel (shipped epilogue), ncu --set full, "
+                                                         "profiles/r02_final_ncu_gemm_and_fused.md (algorithmic 285 MB; "
+                                                         "tensor pipe 82.7 % active)",
                      "peak_source": peak_src, "frac_of_sustained_peak": round(ach / peak_sus, 4),
                      "per_class_us": dom["per_class_us"], "flops_per_launch_avg": dom["flops_avg"],
                      "share_of_step": round(8 * dom["sum_ms"] / step_ms, 3),

@@ -719,8 +719,10 @@ extern "C" int otb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, in
                                  int D, void* stream) {
   OTB_CHECK_ARG(dy && x && mean && rstd && gamma && rows > 0 && D > 0, "otb_layernorm_bwd: bad argument");
   OTB_CHECK_ARG(D % 8 == 0 && lddy % 8 == 0 && ldx % 8 == 0, "otb_layernorm_bwd: D/ld must be multiples of 8");
-  if (ln_fused_enabled() && D <= 4096 && dx != nullptr && (dgamma != nullptr || dbeta != nullptr)) {
-    OTB_CHECK_ARG(lddx % 8 == 0 && (add == nullptr || ldadd % 8 == 0), "otb_layernorm_bwd: bad ld");
+  // dx == nullptr (perceiver norm_media: the frozen CLIP features need no input gradient) takes the one-pass kernel too:
+  // it then only produces the gamma / beta partials (r02 final launch list: the three-kernel fallback cost 34 us per call)
+  if (ln_fused_enabled() && D <= 4096 && (dgamma != nullptr || dbeta != nullptr)) {
+    OTB_CHECK_ARG((dx == nullptr || lddx % 8 == 0) && (add == nullptr || ldadd % 8 == 0), "otb_layernorm_bwd: bad ld");
     OTB_CHECK_ARG(ws != nullptr, "otb_layernorm_bwd: workspace required for parameter gradients");
     const int grid = ln_fused_grid(rows);
     auto kern = (D <= 2048) ? ln_bwd_fused_kernel<1> : ln_bwd_fused_kernel<2>;
