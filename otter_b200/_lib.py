@@ -108,6 +108,11 @@ SIGNATURES = {
     "otb_im2col_patches": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _I, _VP]),
     "otb_clip_assemble": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "otb_media_from_clip": (_I, [_VP, _VP, _I, _VP, _I, _I, _I, _VP]),
+    "otb_rmsnorm_fwd": (_I, [_VP, _I64, _VP, _VP, _I64, _VP, _I, _I, _F, _VP]),
+    "otb_rmsnorm_bwd": (_I, [_VP, _I64, _VP, _I64, _VP, _VP, _VP, _I64, _VP, _I64, _I, _I, _VP]),
+    "otb_rope128": (_I, [_VP, _I64, _I64, _I, _I, _I, _F, _I, _VP]),
+    "otb_swiglu_fwd": (_I, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I, _VP]),
+    "otb_swiglu_bwd": (_I, [_VP, _I64, _VP, _I64, _VP, _I64, _VP, _I64, _VP, _I64, _I64, _I, _VP]),
     "otb_qkln_rope_ws_floats": (_I, []),
     "otb_qkln_rope_fwd": (_I, [_VP, _I64, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _I64, _I, _I, _I, _F, _F, _VP]),
     "otb_qkln_rope_bwd": (_I, [_VP, _I64, _VP, _I64, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _I, _VP, _I64, _I, _I,

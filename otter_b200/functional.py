@@ -481,6 +481,61 @@ def fuyu_scatter(word, cont, idx, b_off):
 
 
 # ------------------------------------------------------------------------------------------------
+# LLaMA layer: RMSNorm, rotary embedding, SwiGLU (csrc/otb_llama.cu)
+# ------------------------------------------------------------------------------------------------
+@_on_device
+def rmsnorm_fwd(x, weight, eps, want_rstd=True):
+    x2 = _mat(x, "x")
+    rows, D = x2.shape
+    y = torch.empty((rows, D), device=x.device, dtype=BF16)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_rstd else None
+    check(_lib.load().otb_rmsnorm_fwd(_p(x2), x2.stride(0), _p(_req(weight, torch.float32, "weight")), _p(y), y.stride(0),
+                                      _p(rstd), rows, D, float(eps), _stream()), "otb_rmsnorm_fwd")
+    return y, rstd
+
+
+@_on_device
+def rmsnorm_bwd(dy, x, rstd, weight, add=None):
+    dy2, x2 = _mat(dy, "dy"), _mat(x, "x")
+    rows, D = x2.shape
+    dx = torch.empty((rows, D), device=x.device, dtype=BF16)
+    add2 = _mat(add, "add") if add is not None else None
+    check(_lib.load().otb_rmsnorm_bwd(_p(dy2), dy2.stride(0), _p(x2), x2.stride(0), _p(rstd), _p(weight), _p(add2),
+                                      add2.stride(0) if add2 is not None else 0, _p(dx), dx.stride(0), rows, D, _stream()),
+          "otb_rmsnorm_bwd")
+    return dx
+
+
+@_on_device
+def rope128_(buf, H, S, nblk, rope_theta, backward=False):
+    """In place: rotary embedding (rotate_half convention) on the first `nblk` blocks of H x 128 columns of buf."""
+    buf = _mat(buf, "buf")
+    check(_lib.load().otb_rope128(_p(buf), buf.stride(0), buf.shape[0], H, S, nblk, float(rope_theta), int(bool(backward)),
+                                  _stream()), "otb_rope128")
+    return buf
+
+
+@_on_device
+def swiglu_fwd(g, u):
+    g, u = _mat(g, "g"), _mat(u, "u")
+    rows, I = g.shape
+    h = torch.empty((rows, I), device=g.device, dtype=BF16)
+    check(_lib.load().otb_swiglu_fwd(_p(g), g.stride(0), _p(u), u.stride(0), _p(h), h.stride(0), rows, I, _stream()),
+          "otb_swiglu_fwd")
+    return h
+
+
+@_on_device
+def swiglu_bwd(dh, g, u):
+    dh, g, u = _mat(dh, "dh"), _mat(g, "g"), _mat(u, "u")
+    rows, I = g.shape
+    dg, du = torch.empty((rows, I), device=g.device, dtype=BF16), torch.empty((rows, I), device=g.device, dtype=BF16)
+    check(_lib.load().otb_swiglu_bwd(_p(dh), dh.stride(0), _p(g), g.stride(0), _p(u), u.stride(0), _p(dg), dg.stride(0),
+                                     _p(du), du.stride(0), rows, I, _stream()), "otb_swiglu_bwd")
+    return dg, du
+
+
+# ------------------------------------------------------------------------------------------------
 # Persimmon / Fuyu layer: split + qk-LayerNorm + partial RoPE (csrc/otb_persimmon.cu)
 # ------------------------------------------------------------------------------------------------
 @_on_device
