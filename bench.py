@@ -547,22 +547,43 @@ class _BenchTokenizer:
         return self.base + len(self.vocab)
 
 
-def m2_dropin_times(dev, batch, L, steps=5):
-    """Harness mode M2: the full drop-in OtterForConditionalGeneration at the OTTER-Image-MPT7B shape —
-    CLIP ViT-L/14 + perceiver + 32 frozen MPT layers (D 4096, 32 heads, ALiBi) with a gated block before every 4th,
-    tied 50432-token LM head, shifted cross-entropy — through the reference's forward() signature, forward + backward,
-    eager launches (the HF module plumbing is not graph-captured)."""
+class _BenchLlamaTokenizer(_BenchTokenizer):
+    def __init__(self):
+        super().__init__(base=32000)
+
+
+def m2_dropin_times(dev, batch, L, steps=5, lm="mpt", frames=1):
+    """Harness mode M2: the full drop-in OtterForConditionalGeneration through the reference's forward()
+    signature, forward + backward, eager launches (the HF module plumbing is not graph-captured).
+      lm="mpt":   OTTER-Image-MPT7B shape — CLIP ViT-L/14 + perceiver + 32 frozen MPT layers (D 4096, 32 heads, ALiBi) with a
+                  gated block before every 4th, tied 50432-token LM head, shifted cross-entropy (otter_b200.lm_mpt).
+      lm="llama": OTTER-Video-LLaMA7B shape (BASELINE configs[2]) — `frames` frames per sample, 32 frozen LLaMA layers
+                  (otter_b200.lm_llama inside HF's LlamaForCausalLM shell; trainable embeddings + LM head as in the
+                  reference, modeling_otter.py:897-905), under autocast(bf16) like the reference's accelerate recipe."""
     from otter_b200 import otter_hf
-    otter_hf.AutoTokenizer = _BenchTokenizer
+    otter_hf.AutoTokenizer = _BenchTokenizer if lm == "mpt" else _BenchLlamaTokenizer
     torch.manual_seed(SEED)
-    text = dict(d_model=4096, n_heads=32, n_layers=32, expansion_ratio=4, max_seq_len=2048, vocab_size=50432, no_bias=True,
-                attn_config=dict(attn_impl="torch", alibi=True, alibi_bias_max=8), architectures=["MPTForCausalLM"],
-                tie_word_embeddings=True, init_device="cpu")
+    extra = {}
+    if lm == "mpt":
+        text = dict(d_model=4096, n_heads=32, n_layers=32, expansion_ratio=4, max_seq_len=2048, vocab_size=50432, no_bias=True,
+                    attn_config=dict(attn_impl="torch", alibi=True, alibi_bias_max=8), architectures=["MPTForCausalLM"],
+                    tie_word_embeddings=True, init_device="cpu")
+        vocab_hi, head_vocab, mlp_mult = 50000, 50432, 8
+    else:
+        text = dict(model_type="llama", hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                    num_attention_heads=32, num_key_value_heads=32, vocab_size=32004, max_position_embeddings=2048,
+                    architectures=["LlamaForCausalLM"], tie_word_embeddings=False)
+        vocab_hi, head_vocab, mlp_mult = 31000, 32004, 3 * 11008 / 4096
+        extra = dict(max_num_frames=128)
     vis = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16, image_size=224,
                patch_size=14, hidden_act="quick_gelu")
     with torch.device(dev):
         model = otter_hf.OtterForConditionalGeneration(otter_hf.OtterConfig(vision_config=vis, text_config=text,
-                                                                             cross_attn_every_n_layers=4))
+                                                                             cross_attn_every_n_layers=4, **extra))
+    if lm == "llama":
+        from otter_b200.lm_llama import FrozenLlamaDecoderLayer
+        n_native = sum(isinstance(m_, FrozenLlamaDecoderLayer) for m_ in model.modules())
+        assert n_native == 32, f"expected 32 otter_b200 LLaMA layers, found {n_native}"
     with torch.no_grad():
         for n_, p_ in model.named_parameters():
             if n_.endswith("attn_gate") or n_.endswith("ff_gate"):
@@ -571,8 +592,8 @@ def m2_dropin_times(dev, batch, L, steps=5):
                 p_.normal_(0.0, 0.02)
     model.train()
     g = torch.Generator().manual_seed(SEED)
-    vision_x = torch.randn(batch, 1, 1, 3, 224, 224, generator=g).to(torch.bfloat16).to(dev)
-    lang_x = torch.randint(3, 50000, (batch, L), generator=g).to(dev)
+    vision_x = torch.randn(batch, 1, frames, 3, 224, 224, generator=g).to(torch.bfloat16).to(dev)
+    lang_x = torch.randint(3, vocab_hi, (batch, L), generator=g).to(dev)
     lang_x[:, 0] = model.media_token_id
     labels = lang_x.clone()
     labels[:, 0] = -100
@@ -582,7 +603,8 @@ def m2_dropin_times(dev, batch, L, steps=5):
     def one():
         for p_ in trainable:
             p_.grad = None
-        out = model(vision_x=vision_x, lang_x=lang_x, attention_mask=mask, labels=labels)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(lm == "llama")):
+            out = model(vision_x=vision_x, lang_x=lang_x, attention_mask=mask, labels=labels)
         out.loss.backward()
         return out.loss
 
@@ -596,11 +618,13 @@ def m2_dropin_times(dev, batch, L, steps=5):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    lm_flops = 2 * 32 * 12 * 4096 * 4096 * 2 + 2 * 2 * 50432 * 4096 * 1.5       # per token: fwd + dgrad (+ LM head fwd+dgrad+wgrad)
+    # per token: fwd + dgrad of the 32 frozen layers (4 + mlp_mult D x D matrices each) + LM head fwd + dgrad + wgrad
+    lm_flops = 2 * 32 * (4 + mlp_mult) * 4096 * 4096 * 2 + 2 * 3 * head_vocab * 4096
     res = {"samples_per_s": round(batch / (ms * 1e-3), 1), "ms_per_step": round(ms, 2), "per_gpu_batch": batch, "L": L,
            "steps": steps, "loss": round(float(loss), 4), "launch": "eager",
            "trainable_params": sum(p_.numel() for p_ in trainable),
-           "algorithmic_tflops": round((flops_per_sample(L) + lm_flops * L) * batch / (ms * 1e-3) / 1e12, 1)}
+           "lm": lm, "frames": frames,
+           "algorithmic_tflops": round((flops_per_sample(L, Fr=frames) + lm_flops * L) * batch / (ms * 1e-3) / 1e12, 1)}
     del model, trainable
     return res
 
@@ -646,6 +670,14 @@ def run_extras(dev, rank, world, args, log):
             torch.cuda.empty_cache()
         except Exception as e:
             extras["m2_dropin_otter_mpt7b"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        try:
+            from otter_b200 import params as P
+            extras["m2_dropin_otter_video_llama7b"] = m2_dropin_times(dev, 4, BASE_CFG["L"], lm="llama", frames=8)
+            log(f"extra M2 drop-in (LLaMA-7B, 8 frames): {extras['m2_dropin_otter_video_llama7b']['ms_per_step']} ms/step")
+            P.clear_caches()
+            torch.cuda.empty_cache()
+        except Exception as e:
+            extras["m2_dropin_otter_video_llama7b"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return extras
 
 

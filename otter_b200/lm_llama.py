@@ -9,7 +9,11 @@ The layer is FROZEN in Otter (modeling_otter.py:897-905): backward produces the 
      -> causal attention (otb_lm_attn_*, no key bias) -> o_proj GEMM (+residual)
      -> RMSNorm -> gate / up GEMMs -> silu(g) * u -> down GEMM (+residual)
 head_dim must be 128 (LLaMA-7B: 4096 = 32 x 128); training path (no KV cache); default position ids.
-`swap_llama_layers(model)` replaces the decoder layers of an HF `LlamaForCausalLM` by this class, sharing the weights.
+`swap_llama_layers(model)` replaces the decoder layers of an HF `LlamaForCausalLM` by this class, sharing the Parameter
+objects.  Attention masks: the kernel applies the causal mask only, which equals HF's causal + padding mask at every
+non-pad position when padding is on the RIGHT (the training collate); a forward pre-hook on the LlamaModel
+checks the 2-D mask once per forward and raises on left padding.  Incremental decoding with a KV cache (generation — out of
+the hot path, SURVEY.md §8 "out of scope") is handed to the original HF layer, which is what the reference itself runs.
 """
 import math
 
@@ -106,7 +110,13 @@ class FrozenLlamaDecoderLayer(nn.Module):
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None, past_key_values=None,
                 output_attentions=False, use_cache=False, **kwargs):
         if past_key_value is not None or past_key_values is not None:
-            raise NotImplementedError("FrozenLlamaDecoderLayer: training path only (no KV cache)")
+            hf = self.__dict__.get("_hf_layer")
+            if hf is None:
+                raise NotImplementedError("FrozenLlamaDecoderLayer: training path only (no KV cache)")
+            kw = dict(kwargs, attention_mask=attention_mask, position_ids=position_ids, use_cache=use_cache)
+            kw["past_key_values" if past_key_values is not None else "past_key_value"] = \
+                past_key_values if past_key_values is not None else past_key_value
+            return hf(hidden_states, **kw)
         if output_attentions:
             raise NotImplementedError("output_attentions is not available from the fused attention kernel")
         B, S, _ = hidden_states.shape
@@ -119,15 +129,55 @@ class FrozenLlamaDecoderLayer(nn.Module):
         return y.to(hidden_states.dtype)          # HF 5.x decoder layers return the tensor
 
 
-def swap_llama_layers(llama_model):
-    """Replace the decoder layers of an HF LlamaForCausalLM / LlamaModel by FrozenLlamaDecoderLayer (weights shared)."""
+def _share_parameters(new, old):
+    for name, _ in list(new.named_parameters()):
+        mod_path, _, leaf = name.rpartition(".")
+        src, dst = old.get_submodule(mod_path), new.get_submodule(mod_path)
+        p = getattr(src, leaf)
+        if tuple(p.shape) != tuple(getattr(dst, leaf).shape):
+            raise ValueError(f"{name}: shape {tuple(p.shape)} does not fit FrozenLlamaDecoderLayer")
+        dst._parameters[leaf] = p          # the SAME Parameter object: .to() / optimizer / checkpoint see one tensor
+
+
+def _right_padding_check(module, args, kwargs):
+    mask = kwargs.get("attention_mask")
+    if mask is not None and mask.dim() == 2 and mask.shape[1] > 1:
+        m = mask.to(torch.bool)
+        if bool((m[:, 1:] & ~m[:, :-1]).any()):
+            raise NotImplementedError("FrozenLlamaDecoderLayer applies the causal mask only: attention_mask must be "
+                                      "right-padded (ones then zeros per row)")
+    elif mask is not None and not isinstance(mask, dict) and mask.dim() != 2:
+        raise NotImplementedError("FrozenLlamaDecoderLayer: pass the 2-D padding mask, not a prepared 4-D mask")
+    return None
+
+
+def swappable(cfg):
+    """True when the HF LlamaConfig describes layers this module covers (MHA, head_dim 128, default RoPE, no biases)."""
+    rp = getattr(cfg, "rope_parameters", None) or {}
+    rope_type = rp.get("rope_type", "default") if isinstance(rp, dict) else "default"
+    hd = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
+    return (hd == 128 and cfg.hidden_size == cfg.num_attention_heads * 128
+            and getattr(cfg, "num_key_value_heads", cfg.num_attention_heads) == cfg.num_attention_heads
+            and rope_type == "default" and not getattr(cfg, "attention_bias", False) and not getattr(cfg, "mlp_bias", False)
+            and getattr(cfg, "hidden_act", "silu") == "silu" and cfg.hidden_size % 64 == 0 and cfg.intermediate_size % 64 == 0)
+
+
+def swap_llama_layers(llama_model, keep_hf_for_cache=True):
+    """Replace the decoder layers of an HF LlamaForCausalLM / LlamaModel by FrozenLlamaDecoderLayer (Parameters shared)."""
     model = llama_model.model if hasattr(llama_model, "model") else llama_model
     cfg = model.config
+    if not swappable(cfg):
+        raise ValueError("swap_llama_layers: this LlamaConfig is outside FrozenLlamaDecoderLayer's coverage (see swappable())")
     rp = getattr(cfg, "rope_parameters", None) or {}
     theta = rp.get("rope_theta", getattr(cfg, "rope_theta", 10000.0))
     for i, old in enumerate(model.layers):
         new = FrozenLlamaDecoderLayer(cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size, cfg.rms_norm_eps, theta)
-        new.load_state_dict(old.state_dict(), strict=True, assign=True)
+        _share_parameters(new, old)
         new.requires_grad_(False)
+        if keep_hf_for_cache:
+            new.__dict__["_hf_layer"] = old            # not a registered sub-module: no duplicate state-dict keys
         model.layers[i] = new
+    if not getattr(model, "_otb_mask_hook", False):
+        model.register_forward_pre_hook(_right_padding_check, with_kwargs=True)
+        model._otb_mask_hook = True
     return llama_model

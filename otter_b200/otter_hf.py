@@ -8,6 +8,7 @@ reference's own MPT / MosaicGPT / Falcon classes when the reference package is i
 hot path.
 """
 import copy
+import os
 from typing import List, Optional
 
 import torch
@@ -95,7 +96,11 @@ def _build_lang_encoder(text_config):
     arch = (getattr(text_config, "architectures", None) or ["LlamaForCausalLM"])[0]
     if "llama" in name or arch == "LlamaForCausalLM":
         from transformers import LlamaForCausalLM
-        return LlamaForCausalLM(config=text_config), name
+        from . import lm_llama
+        lm = LlamaForCausalLM(config=text_config)
+        if os.environ.get("OTB_LLAMA_LAYERS", "1") != "0" and lm_llama.swappable(text_config):
+            lm_llama.swap_llama_layers(lm)     # frozen decoder layers on the otter_b200 kernels
+        return lm, name
     _, cls, tok = _reference_lm(arch)
     return cls(config=text_config), tok
 

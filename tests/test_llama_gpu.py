@@ -88,10 +88,22 @@ def test_swap_llama_layers_in_an_hf_model():
     torch.manual_seed(0)
     model = LlamaForCausalLM(cfg).to(DEV)
     ids = torch.randint(0, 64, (2, 40), device=DEV)
+    mask = torch.ones_like(ids)
+    mask[1, 30:] = 0                                                                      # right padding
     with torch.no_grad():
-        ref = model(input_ids=ids).logits.float()
+        ref = model(input_ids=ids, attention_mask=mask, use_cache=False).logits.float()
+    keys = set(model.state_dict().keys())
     swap_llama_layers(model)
+    assert set(model.state_dict().keys()) == keys                                         # checkpoint-compatible
     assert all(isinstance(l, FrozenLlamaDecoderLayer) for l in model.model.layers)
     with torch.no_grad():
-        got = model(input_ids=ids).logits.float()
-    assert _rel(got, ref) <= 2e-2, _rel(got, ref)
+        got = model(input_ids=ids, attention_mask=mask, use_cache=False).logits.float()
+    valid = mask.bool()
+    assert _rel(got[valid], ref[valid]) <= 2e-2, _rel(got[valid], ref[valid])
+    # incremental decoding with a KV cache is handed to the HF layer the reference itself runs
+    with torch.no_grad():
+        out = model(input_ids=ids[:1], use_cache=True)
+    assert out.past_key_values is not None and _rel(out.logits, ref[:1]) <= 2e-2
+    left = mask.flip(1)
+    with pytest.raises(NotImplementedError):
+        model(input_ids=ids, attention_mask=left, use_cache=False)
