@@ -239,6 +239,21 @@ int otb_attn_fwd_f32(const otb_attn_desc* d, void* stream);
 int otb_epilogue_f32(const float* acc, const float* bias, int act, const float* scale_ptr, int scale_tanh,
                      const float* residual, float* out, int M, int N, void* stream);
 
+/* fp32-grade BACKWARD passes (csrc/otb_fp32_bwd.cu; dgrad / wgrad reuse the split GEMM): gradients of the path within 1e-3
+ * of the reference's fp32 autograd.  All matrices fp32; deterministic (no atomics).
+ *   otb_layernorm_bwd_f32  dx (may be NULL) and dgamma / dbeta (both or neither); ws: fp32 [2*rows] scratch
+ *   otb_act_bwd_f32        out = dy * act'(pre), act 1 = exact GELU, 2 = quick-GELU
+ *   otb_gate_grad_f32      out[0] = (1 - tanh(*gate)^2) * sum(dy * f)     (modeling_otter.py:380-389, the two tanh gates)
+ *   otb_rowbias_grad_f32   gradient of otb_add_rowbias_f32's table: out [out_rows][D], rows >= mod are zero
+ *   otb_attn_bwd_f32       d as for otb_attn_fwd_f32 with d->out = the forward output; g holds fp32 dout / dq / dkv1 / dkv2
+ *                          (dK at dk*_col0 + h*64, dV at dv*_col0 + h*64) and g->dq_ws = fp32 [P*H*Sq*3] scratch */
+int otb_layernorm_bwd_f32(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma, float* dx,
+                          int64_t lddx, float* dgamma, float* dbeta, float* ws, int rows, int D, float eps, void* stream);
+int otb_act_bwd_f32(const float* dy, const float* pre, int act, float* out, int64_t n, void* stream);
+int otb_gate_grad_f32(const float* dy, const float* f, int64_t n, const float* gate, float* out, void* stream);
+int otb_rowbias_grad_f32(const float* dy, int div, int mod, int rows, int D, int out_rows, float* out, void* stream);
+int otb_attn_bwd_f32(const otb_attn_desc* d, const otb_attn_grads* g, void* stream);
+
 /* CLIP embeddings (xformers_model/clip.py:73-81): */
 /* im2col of non-overlapping patches: pixels [N][3][H][W] (fp32 if pix_fp32 else bf16) ->
  * out bf16 [N*(H/p)*(W/p)][Kpad], column c*p*p + i*p + j, zero padded to Kpad. */

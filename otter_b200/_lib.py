@@ -102,6 +102,11 @@ SIGNATURES = {
     "otb_add_rowbias_f32": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP]),
     "otb_attn_fwd_f32": (_I, [C.POINTER(AttnDesc), _VP]),
     "otb_epilogue_f32": (_I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _I, _I, _VP]),
+    "otb_layernorm_bwd_f32": (_I, [_VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _VP, _VP, _I, _I, _F, _VP]),
+    "otb_act_bwd_f32": (_I, [_VP, _VP, _I, _VP, _I64, _VP]),
+    "otb_gate_grad_f32": (_I, [_VP, _VP, _I64, _VP, _VP, _VP]),
+    "otb_rowbias_grad_f32": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP]),
+    "otb_attn_bwd_f32": (_I, [C.POINTER(AttnDesc), C.POINTER(AttnGrads), _VP]),
     "otb_label_mask": (_I, [_VP, _I, _I, _I64, _I64, _I64, _I64, _VP, _VP]),
     "otb_shifted_cross_entropy": (_I, [_VP, _I, _I64, _VP, _I, _I, _I, _VP, _VP, _I64, _VP, _VP]),
     "otb_scale_by_scalar": (_I, [_VP, _I, _I64, _VP, _VP]),

@@ -654,5 +654,69 @@ def attn_fwd_f32(spec):
     return out
 
 
+# ---- fp32-grade backward passes (csrc/otb_fp32_bwd.cu) ----
+@_on_device
+def layernorm_bwd_f32(dy, x, gamma, eps=1e-5, need_dx=True, need_params=True):
+    dy2, x2 = _mat(dy, "dy", torch.float32), _mat(x, "x", torch.float32)
+    rows, D = x2.shape
+    dx = torch.empty((rows, D), device=x.device, dtype=torch.float32) if need_dx else None
+    dg = torch.empty(D, device=x.device, dtype=torch.float32) if need_params else None
+    db = torch.empty(D, device=x.device, dtype=torch.float32) if need_params else None
+    ws = torch.empty(2 * rows, device=x.device, dtype=torch.float32)
+    check(_lib.load().otb_layernorm_bwd_f32(_p(dy2), dy2.stride(0), _p(x2), x2.stride(0), _p(_req(gamma, torch.float32)),
+                                            _p(dx), D, _p(dg), _p(db), _p(ws), rows, D, eps, _stream()),
+          "otb_layernorm_bwd_f32")
+    return dx, dg, db
+
+
+@_on_device
+def act_bwd_f32(dy, pre, act):
+    dy, pre = _req(dy, torch.float32, "dy").contiguous(), _req(pre, torch.float32, "pre").contiguous()
+    out = torch.empty_like(pre)
+    check(_lib.load().otb_act_bwd_f32(_p(dy), _p(pre), act, _p(out), pre.numel(), _stream()), "otb_act_bwd_f32")
+    return out
+
+
+@_on_device
+def gate_grad_f32(dy, f, gate):
+    dy, f = _req(dy, torch.float32, "dy").contiguous(), _req(f, torch.float32, "f").contiguous()
+    out = torch.empty(1, device=dy.device, dtype=torch.float32)
+    check(_lib.load().otb_gate_grad_f32(_p(dy), _p(f), f.numel(), _p(_req(gate, torch.float32)), _p(out), _stream()),
+          "otb_gate_grad_f32")
+    return out
+
+
+@_on_device
+def rowbias_grad_f32(dy, div, mod, out_rows):
+    dy2 = _mat(dy, "dy", torch.float32)
+    assert dy2.is_contiguous()
+    rows, D = dy2.shape
+    out = torch.empty((out_rows, D), device=dy.device, dtype=torch.float32)
+    check(_lib.load().otb_rowbias_grad_f32(_p(dy2), div, mod, rows, D, out_rows, _p(out), _stream()), "otb_rowbias_grad_f32")
+    return out
+
+
+@_on_device
+def attn_bwd_f32(spec, out, dout):
+    """spec: AttnSpec(dtype=torch.float32) of the forward problem (K at column 0, V at column H*64 of each key source),
+    out: its forward output -> (dq [P*Sq, H*64], dkv1 [P*Sk1, 2*H*64], dkv2 or None), all fp32."""
+    inner = spec.H * 64
+    dev = spec.q.device
+    dout = _mat(dout, "dout", torch.float32)
+    dq = torch.empty((spec.P * spec.Sq, inner), device=dev, dtype=torch.float32)
+    dkv1 = torch.empty((spec.P * spec.Sk1, 2 * inner), device=dev, dtype=torch.float32)
+    dkv2 = torch.empty((spec.P * spec.Sk2, 2 * inner), device=dev, dtype=torch.float32) if spec.Sk2 else None
+    ws = torch.empty(spec.P * spec.H * spec.Sq * 3, device=dev, dtype=torch.float32)
+    d = spec.desc(out, 0, None)
+    g = AttnGrads()
+    g.dout, g.dq, g.dkv1, g.dkv2, g.dq_ws = _p(dout), _p(dq), _p(dkv1), _p(dkv2), _p(ws)
+    g.ld_dout, g.ld_dq, g.ld_dkv1 = dout.stride(0), dq.stride(0), dkv1.stride(0)
+    g.ld_dkv2 = dkv2.stride(0) if dkv2 is not None else 0
+    g.dout_cols, g.dout_col0, g.dq_col0 = dout.shape[1], 0, 0
+    g.dk1_col0, g.dv1_col0, g.dk2_col0, g.dv2_col0 = 0, inner, 0, inner
+    check(_lib.load().otb_attn_bwd_f32(C.byref(d), C.byref(g), _stream()), "otb_attn_bwd_f32")
+    return dq, dkv1, dkv2
+
+
 def launch_count():
     return int(_lib.load().otb_launch_count())

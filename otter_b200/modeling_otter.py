@@ -89,7 +89,6 @@ class OtterPerceiverBlock(nn.Module):
         """x (b, T, n1, D) media features, latents (b, T, n2, D) -> (b, T, n2, D)."""
         b, T, n2, D = latents.shape
         if fp32_path.is_fp32():
-            fp32_path.require_no_grad(x, latents, *self.parameters())
             out = fp32_path.perceiver_block(self, fp32_path._f32_2d(x, D), fp32_path._f32_2d(latents, D), b * T)
             return out.view(b, T, n2, D).to(latents.dtype)
         out = self._apply2d(_as_bf16_2d(x, D), _as_bf16_2d(latents, D), b * T, x.requires_grad)
@@ -124,7 +123,6 @@ class OtterPerceiverResampler(nn.Module):
         """x (b, T, F, v, D) -> (b, T, n, D)."""
         b, T, Fr, v, D = x.shape
         if fp32_path.is_fp32():
-            fp32_path.require_no_grad(x, *self.parameters())
             return fp32_path.resampler_forward(self, x).to(x.dtype)
         media = _as_bf16_2d(x, D)
         if exists(self.frame_embs):                                                    # :224-226
@@ -167,7 +165,6 @@ class OtterMaskedCrossAttention(nn.Module):
         _, T_img, n = media.shape[:3]
         tt = _text_time_for(media_locations, attend_previous)
         if fp32_path.is_fp32():
-            fp32_path.require_no_grad(x, media, *self.parameters())
             out = fp32_path.masked_cross_attention(self, fp32_path._f32_2d(x, D),
                                                    fp32_path._f32_2d(media, media.shape[-1]), tt, B, L, T_img, n)
             return out.view(B, L, D).to(x.dtype)
@@ -206,7 +203,6 @@ class OtterGatedCrossAttentionBlock(nn.Module):
         _, T_img, n = media.shape[:3]
         tt = _text_time_for(media_locations, attend_previous)
         if fp32_path.is_fp32():
-            fp32_path.require_no_grad(x, media, *self.parameters())
             out = fp32_path.gated_block(self, fp32_path._f32_2d(x, D), fp32_path._f32_2d(media, media.shape[-1]), tt,
                                         B, L, T_img, n)
             return out.view(B, L, D).to(x.dtype)
@@ -342,7 +338,8 @@ def encode_vision_x(vision_encoder, perceiver, vision_x):
     b, T, Fr = vision_x.shape[:3]
     pixels = vision_x.reshape(b * T * Fr, *vision_x.shape[3:])
     if fp32_path.is_fp32() and isinstance(vision_encoder, CLIPVisionModel):
-        feats = fp32_path.clip_last_hidden(vision_encoder, pixels)[:, 1:, :]
+        with torch.no_grad():                                                  # frozen tower, as on the bf16 path
+            feats = fp32_path.clip_last_hidden(vision_encoder, pixels)[:, 1:, :]
         return perceiver(feats.reshape(b, T, Fr, feats.shape[1], feats.shape[2]))
     if isinstance(vision_encoder, CLIPVisionModel):
         hidden = vision_encoder.last_hidden_bf16(pixels)                       # bf16 [bTF, 1+v, D]

@@ -280,12 +280,15 @@ def test_fp32_mode_north_star_tolerance():
             assert (err > 1e-5 * ref.abs().max() + NS_RTOL * ref.abs()).sum().item() == 0, (tag, err.max().item())
 
 
-def test_fp32_mode_is_forward_only():
+def test_fp32_mode_clip_is_forward_only():
+    """The trainable blocks have an fp32-grade backward (tests/test_fp32_backward_gpu.py); the frozen CLIP tower does not."""
     import otter_b200
-    from otter_b200.modeling_otter import OtterPerceiverBlock
-    blk = OtterPerceiverBlock(dim=128).to(DEV)
+    from transformers import CLIPVisionConfig
+    from otter_b200.modeling_clip import CLIPVisionModel
+    clip = CLIPVisionModel(CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=1, num_attention_heads=2,
+                                            image_size=28, patch_size=14, hidden_act="quick_gelu")).to(DEV)
     with otter_b200.precision("fp32"), pytest.raises(RuntimeError, match="forward-only"):
-        blk(torch.randn(1, 1, 64, 128, device=DEV), torch.randn(1, 1, 64, 128, device=DEV))
+        clip(torch.randn(1, 3, 28, 28, device=DEV))
 
 
 @torch.no_grad()
