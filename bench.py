@@ -161,7 +161,8 @@ class HotPath:
             direct = [m.weight for mod in (self.perceiver, self.gated) for m in mod.modules()
                       if isinstance(m, torch.nn.Linear)]
         self.flat = FlatGradBuffer(self.trainable, device=dev, comm_dtype=comm_dtype,
-                                   nccl_registered=args.nccl_registered and world > 1, direct_params=direct)
+                                   nccl_registered=args.nccl_registered and world > 1, direct_params=direct,
+                                   reduce_op=args.reduce_op)
         self.h_vis, self.h_hid, self.h_loc = host_batch(batch, rank, cfg)
         self.d_vis, self.d_hid, self.d_loc = self.h_vis.to(dev), self.h_hid.to(dev), self.h_loc.to(dev)
         self.loss_host = torch.zeros(1).pin_memory()
@@ -809,7 +810,8 @@ def run_cuda(args):
                                "after it" if comm_mode == "bf16-direct" else ""),
                    "cache": "per-step working set (2.4 GB bf16 weights + activations) >> 126 MB L2; no explicit flush",
                    "grad_allreduce_bytes": comm_bytes,
-                   "grad_allreduce_dtype": comm_mode, "nccl_registered_buffer": bool(args.nccl_registered)},
+                   "grad_allreduce_dtype": comm_mode, "nccl_registered_buffer": bool(args.nccl_registered),
+                   "grad_allreduce_op": ("sum, 1/N folded into the up-cast" if (args.reduce_op == "sum" and comm_mode != "fp32") else "avg")},
         "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "ms_per_step": round(ms_e2e / args.steps, 3),
                 "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "h2d_overlapped_with_previous_step": bool(args.e2e_prefetch)},
@@ -1029,6 +1031,9 @@ def main():
                          "epilogues write the wire buffer (one up-cast after the collective).  auto = bf16-direct for N > 1")
     ap.add_argument("--e2e-prefetch", action="store_true",
                     help="e2e leg: copy the next step's inputs host->device on a copy stream while this step computes")
+    ap.add_argument("--reduce-op", default="sum", choices=["sum", "avg"],
+                    help="reduction of the wire-format all-reduce: sum (1/N folded into the up-cast; lets NCCL use its "
+                         "in-switch NVLS algorithms) or avg (ncclAvg = pre-multiplied sum, RING only)")
     ap.add_argument("--nccl-registered", action="store_true",
                     help="allocate the flat gradient buffer from NCCL's allocator and register it (zero-copy / NVLS)")
     ap.add_argument("--seq-len", type=int, default=256, help="text length L (SURVEY.md §8d sweeps 128/256/512/1024)")

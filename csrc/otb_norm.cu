@@ -422,6 +422,22 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
     }
   }
 }
+// dst = float(src) * scale : the up-cast after a reduced-precision all-reduce(SUM), with the 1/world_size folded in
+__global__ void cast_bf16_f32_scale_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + i)), f);
+      *reinterpret_cast<float4*>(dst + i) = make_float4(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
+      *reinterpret_cast<float4*>(dst + i + 4) = make_float4(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
+    } else {
+      for (long long k = i; k < n; ++k) dst[k] = __bfloat162float(src[k]) * scale;
+    }
+  }
+}
 __global__ void bcast_rows_kernel(const float* __restrict__ src, int div, int mod, bf16* __restrict__ out, int rows,
                                   int D) {
   pdl_launch_dependents();
@@ -789,6 +805,16 @@ extern "C" int otb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* s
   OTB_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
                 "otb_cast_bf16_f32: pointers must be 16-byte aligned");
   OTB_CHECK_CUDA(launch_k(cast_bf16_f32_kernel, dim3(grid_for((n + 7) / 8, 256)), dim3(256), 0, ST(stream), static_cast<const bf16*>(src), dst, n));
+  count_launch();
+  OTB_CHECK_CUDA(cudaGetLastError());
+  return OTB_OK;
+}
+extern "C" int otb_cast_bf16_f32_scale(const void* src, float* dst, int64_t n, float scale, void* stream) {
+  OTB_CHECK_ARG(src && dst && n > 0, "otb_cast_bf16_f32_scale: bad argument");
+  OTB_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                "otb_cast_bf16_f32_scale: pointers must be 16-byte aligned");
+  OTB_CHECK_CUDA(launch_k(cast_bf16_f32_scale_kernel, dim3(grid_for((n + 7) / 8, 256)), dim3(256), 0, ST(stream),
+                          static_cast<const bf16*>(src), dst, (long long)n, scale));
   count_launch();
   OTB_CHECK_CUDA(cudaGetLastError());
   return OTB_OK;

@@ -201,6 +201,8 @@ int otb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, 
 /* dst(bf16)[i] = src(fp32)[i]  — bf16 shadow of fp32 master weights (autocast-equivalent). */
 int otb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int otb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+/* dst = float(src) * scale — the up-cast after a bf16 all-reduce(SUM) with 1/world_size folded in (otter_b200/dp.py). */
+int otb_cast_bf16_f32_scale(const void* src, float* dst, int64_t n, float scale, void* stream);
 /* The same cast for a LIST of tensors in one launch (all trainable weights after an optimizer step).
  * table: device array of n_tensors records {const float* src; bf16* dst; int64 n; int64 first_block}, 32 bytes each,
  * sorted by first_block; tensor t owns blocks [first_block_t, first_block_t + ceil(n_t / 4096)); total_blocks is

@@ -91,6 +91,7 @@ SIGNATURES = {
     "otb_cast_f32_bf16": (_I, [_VP, _VP, _I64, _VP]),
     "otb_cast_f32_bf16_multi": (_I, [_VP, _I, _I64, _VP]),
     "otb_cast_bf16_f32": (_I, [_VP, _VP, _I64, _VP]),
+    "otb_cast_bf16_f32_scale": (_I, [_VP, _VP, _I64, _F, _VP]),
     "otb_bcast_rows": (_I, [_VP, _I, _I, _VP, _I, _I, _VP]),
     "otb_add_rowbias": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP]),
     "otb_grouped_colsum": (_I, [_VP, _I64, _I, _I, _I, _I, _VP, _I, _VP]),

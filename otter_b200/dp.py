@@ -4,8 +4,8 @@ Replaces `accelerator.prepare(model)` + `accelerator.backward(loss)` (DDP bucket
 pipeline/train/instruction_following.py:200,219-222,491-494): the batch dimension
 shards across ranks with no other collective.  Every trainable parameter's `.grad` is a view into one
 contiguous buffer; the wgrad GEMM epilogues write straight into it (`_otb_grad` sink, otter_b200.params),
-so the step ends with a single `all_reduce(AVG)` over NVLink/NVSwitch (NCCL via torch.distributed; on CPU
-tests the same code runs over gloo).
+so the step ends with a single mean all-reduce over NVLink/NVSwitch (NCCL via torch.distributed: `AVG` on the fp32
+buffer, `SUM` with 1/world_size folded into the up-cast on the bf16 wire format; on CPU tests the same code runs over gloo).
 """
 import torch
 import torch.distributed as dist
@@ -22,15 +22,20 @@ class _CommHandle:
     def wait(self):
         if self.work is not None:
             self.work.wait()
+        o = self.owner
+        if self.divide_by and o.comm.is_cuda and o.comm.dtype == torch.bfloat16 and o.flat.dtype == torch.float32:
+            from . import functional as F                      # one pass: up-cast with the 1/world_size folded in
+            F.cast_f32_scaled(o.comm, o.flat, 1.0 / self.divide_by)
+            return True
         if self.divide_by:
-            self.owner.comm.div_(self.divide_by)
-        self.owner.flat.copy_(self.owner.comm)
+            o.comm.div_(self.divide_by)
+        o.flat.copy_(o.comm)
         return True
 
 
 class FlatGradBuffer:
     def __init__(self, params, device=None, dtype=torch.float32, comm_dtype=None, nccl_registered=False,
-                 direct_params=None):
+                 direct_params=None, reduce_op="sum"):
         """direct_params (only with a reduced-precision comm_dtype): parameters whose gradient is produced by ONE wgrad
         GEMM per step (the nn.Linear weights of the perceiver / gated blocks).  Their kernel sink is the bf16 WIRE
         buffer itself — the epilogue rounds once to the wire format, which is also what autocast's backward hands the
@@ -40,6 +45,12 @@ class FlatGradBuffer:
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
+        if reduce_op not in ("sum", "avg"):
+            raise ValueError("reduce_op must be 'sum' or 'avg'")
+        # Wire-format collectives reduce with SUM and fold 1/world_size into the up-cast that follows: NCCL implements AVG
+        # on floating types as pre-multiplied sum, which its in-switch (NVLS) algorithms do not take, so AVG pins the
+        # collective to RING (profiles/r02_scale_check_n4_n8.md).  'avg' keeps ncclAvg.
+        self.reduce_op = reduce_op
         direct_ids = {id(p) for p in (direct_params or [])}
         if direct_ids and (comm_dtype is None or comm_dtype == dtype):
             raise ValueError("direct_params needs a reduced-precision comm_dtype")
@@ -138,6 +149,9 @@ class FlatGradBuffer:
             if d < self.numel:
                 self.comm[d:].copy_(self.flat[d:])
             if dist.get_backend(group) == "gloo":
+                w = dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+                h = _CommHandle(self, w if async_op else None, dist.get_world_size(group))
+            elif self.reduce_op == "sum":
                 w = dist.all_reduce(self.comm, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
                 h = _CommHandle(self, w if async_op else None, dist.get_world_size(group))
             else:

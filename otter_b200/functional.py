@@ -377,6 +377,16 @@ def cast_f32(src, out=None):
 
 
 @_on_device
+def cast_f32_scaled(src, out, scale):
+    """out fp32 = float(src bf16) * scale (flat buffers)."""
+    _req(src, BF16, "src")
+    _req(out, torch.float32, "out")
+    assert src.is_contiguous() and out.is_contiguous() and src.numel() == out.numel()
+    check(_lib.load().otb_cast_bf16_f32_scale(_p(src), _p(out), src.numel(), float(scale), _stream()), "otb_cast_bf16_f32_scale")
+    return out
+
+
+@_on_device
 def bcast_rows(src, rows, div, mod):
     _req(src, torch.float32, "src")
     D = src.shape[-1]

@@ -293,3 +293,14 @@ def test_multi_tensor_cast_matches_per_tensor_cast():
     P.refresh(ps)                                        # second call reuses the pointer table and the shadow buffers
     for p in ps:
         assert torch.equal(P.bf16_of(p), p.detach().to(torch.bfloat16)), p.shape
+
+
+def test_upcast_with_folded_scale():
+    """otb_cast_bf16_f32_scale: the up-cast after the bf16 all-reduce(SUM) with 1/world_size folded in (dp.py)."""
+    from otter_b200 import functional as F
+    g = torch.Generator().manual_seed(5)
+    for n in (8, 4099, 1 << 20):
+        src = torch.randn(n, generator=g).to(torch.bfloat16)
+        out = torch.full((n,), 7.0, device=dev())
+        F.cast_f32_scaled(src.to(dev()), out, 1.0 / 3.0)
+        assert torch.equal(out.cpu(), src.float() * torch.tensor(1.0 / 3.0, dtype=torch.float32))
