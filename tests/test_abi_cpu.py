@@ -71,3 +71,15 @@ def test_sass_is_blackwell_native():
         assert mnemonic in sass, f"{mnemonic} missing from the SASS"
     assert "UTCHMMA.2CTA" in sass or "2CTA" in sass, "cta_group::2 MMA missing"
     assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync (HMMA) found"
+
+
+def test_integration_guide_names_every_entry_point():
+    """INTEGRATION.md's table (entry point -> reference file:line it replaces) covers the whole header."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "otter_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    syms = sorted(set(re.findall(r"\b(otb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(syms) >= 50
+    assert [s for s in syms if s not in doc] == []
