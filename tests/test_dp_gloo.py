@@ -171,3 +171,15 @@ def test_flat_allreduce_world2_bf16_direct_sinks():
     res = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(timeout=60) for p in procs]
     assert all(ok and views for _, ok, views, _ in res), res
+
+
+def test_reduce_op_argument():
+    """The wire-format collective reduces with SUM (1/world_size folded into the up-cast) by default; 'avg' keeps ncclAvg;
+    anything else is rejected.  (On gloo both arms are SUM + divide — the NCCL arms are measured in profiles/r02_reduce_op_n4.md.)"""
+    import pytest
+    from otter_b200.dp import FlatGradBuffer
+    lin = torch.nn.Linear(8, 8)
+    assert FlatGradBuffer(lin.parameters(), device="cpu", comm_dtype=torch.bfloat16).reduce_op == "sum"
+    assert FlatGradBuffer(lin.parameters(), device="cpu", comm_dtype=torch.bfloat16, reduce_op="avg").reduce_op == "avg"
+    with pytest.raises(ValueError, match="reduce_op"):
+        FlatGradBuffer(lin.parameters(), device="cpu", reduce_op="max")
