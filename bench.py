@@ -522,6 +522,32 @@ def fuyu_patch_linear_times(dev):
     return res
 
 
+def allreduce_alone(hp, dev, world, iters=10):
+    """The step's one collective timed on its own (SURVEY.md §8d "NCCL all-reduce timed separately"): CUDA events on the
+    current stream around `iters` back-to-back FlatGradBuffer.all_reduce() calls — cast of the fp32-produced tail, the NCCL
+    all-reduce, the up-cast into the fp32 `.grad` views — nothing overlapped with it, max over ranks.  Bus bandwidth =
+    2 (N-1)/N x wire bytes / time, the figure nccl-tests quotes, to hold against NVLink 5's 900 GB/s per direction."""
+    import torch.distributed as dist
+    for _ in range(2):
+        hp.flat.all_reduce()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        hp.flat.all_reduce()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    nbytes = hp.flat.comm_nbytes()
+    return {"ms": round(ms, 3), "wire_bytes": int(nbytes), "iters": iters,
+            "busbw_gbs": round(2.0 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9, 1),
+            "includes": "tail cast + NCCL all-reduce + up-cast to the fp32 .grad views; not overlapped with compute "
+                        "(inside the step it overlaps the next batch's CLIP forward)"}
+
+
 class _BenchTokenizer:
     """Offline stand-in for the HF tokenizer the model constructor downloads (no network on the box): ids only."""
     pad_token = None
@@ -768,6 +794,13 @@ def run_cuda(args):
             log(f"self-check vs the CPU oracle at batch 1: {check['rel_err']} ok={check['ok']}")
         except Exception as e:
             check = {"ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
+    comm_alone = None
+    if world > 1:                                   # after every timed region: cannot disturb `value` / `e2e`
+        try:
+            comm_alone = allreduce_alone(hp, dev, world)
+            log(f"all-reduce alone: {comm_alone['ms']} ms, bus bandwidth {comm_alone['busbw_gbs']} GB/s")
+        except Exception as e:
+            comm_alone = {"error": f"{type(e).__name__}: {e}"[:200]}
     h2d = hp.h2d_bytes()
     comm_mode = hp.comm_mode
     comm_bytes = hp.flat.comm_nbytes() if world > 1 else 0
@@ -836,6 +869,8 @@ def run_cuda(args):
                                            else "fallback 6600 GB/s", "timing": "CUDA-graph replay, CUDA events, "
                                            "rotating operand sets > L2 (cold operands)", "kernels": hbm_rows}},
     }
+    if comm_alone is not None:
+        out["allreduce_alone"] = comm_alone
     if check is not None:
         out["self_check"] = check
     if extras is not None:
