@@ -38,3 +38,42 @@ def test_reference_arm_json_line(tmp_path):
     assert d["config"]["per_gpu_batch"] == 1 and d["cpu_baseline"]["batch"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["steps"] == 1
+
+
+def test_allreduce_alone_record(monkeypatch):
+    """bench.allreduce_alone (N > 1 only): field names and the bus-bandwidth formula, with CUDA events and the process
+    group replaced by stand-ins (the real thing needs NCCL)."""
+    import torch
+    import torch.distributed as dist
+    import bench
+
+    class _Ev:
+        def __init__(self, enable_timing=True):
+            pass
+
+        def record(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 50.0                     # ms for the 10 iterations
+
+    class _Flat:
+        calls = 0
+
+        def all_reduce(self):
+            _Flat.calls += 1
+
+        def comm_nbytes(self):
+            return 2_000_000_000
+
+    class _HP:
+        flat = _Flat()
+
+    monkeypatch.setattr(torch.cuda, "Event", _Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "all_reduce", lambda t, op=None: None)
+    r = bench.allreduce_alone(_HP(), "cpu", 8, iters=10)
+    assert _Flat.calls == 12                                    # 2 warm-up + 10 timed
+    assert r["ms"] == 5.0 and r["wire_bytes"] == 2_000_000_000 and r["iters"] == 10
+    assert abs(r["busbw_gbs"] - 2 * 7 / 8 * 2e9 / 5e-3 / 1e9) < 0.1      # 700 GB/s
