@@ -158,7 +158,7 @@ ln_bwd_param_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __r
     if (gc < D) ws[(static_cast<long long>(which) * chunks + chunk) * D + gc] = acc;
   }
 }
-// One-pass LayerNorm backward (candidate, OTB_LN_FUSED=1): dx AND the gamma/beta column partials from a single read of
+// One-pass LayerNorm backward (default; OTB_LN_FUSED=0 selects the three-kernel path): dx AND the gamma/beta column partials from a single read of
 // x / dy.  A CTA walks its rows in batches of kLnR; thread t owns the 16 B column vectors t, t+256, ... (VPT of them) of
 // every row, so the parameter partials stay in its registers across all rows of the CTA (deterministic: fixed order,
 // no atomics) and the two row statistics of a batch take one block reduction (double-buffered smem, one barrier).

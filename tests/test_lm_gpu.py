@@ -1,4 +1,4 @@
-"""GPU parity of the §8f rank-1 candidate: causal / ALiBi head-dim-128 attention (otb_lm_attn_fwd / _bwd) and the
+"""GPU parity of §8f rank 1: causal / ALiBi head-dim-128 attention (otb_lm_attn_fwd / _bwd) and the
 frozen MPT block built on it, against fp32 torch math and the reference-pinned oracle (oracle/restatement_lm.py).
 Tolerances are bf16-storage tolerances (inputs, P and outputs are rounded to bf16 in the kernels)."""
 import math
